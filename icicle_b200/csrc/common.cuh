@@ -1,0 +1,184 @@
+// Shared host-side plumbing for the C-ABI translation units: error mapping, stream-ordered scratch buffers,
+// host<->device staging that honours the reference's are_*_on_device flags, and field / curve dispatch.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include "../../include/icicle_b200.h"
+#include "ff.cuh"
+#include "ext.cuh"
+#include "ec.cuh"
+
+namespace b200 {
+
+#define B200_CUDA_TRY(expr, errcode)                                                                                   \
+  do {                                                                                                                 \
+    cudaError_t _e = (expr);                                                                                           \
+    if (_e != cudaSuccess) {                                                                                           \
+      fprintf(stderr, "[icicle_b200] %s:%d %s -> %s\n", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));           \
+      return (errcode);                                                                                                \
+    }                                                                                                                  \
+  } while (0)
+
+static inline int map_alloc_error(cudaError_t e) { return e == cudaErrorMemoryAllocation ? B200_OUT_OF_MEMORY : B200_ALLOCATION_FAILED; }
+
+// Stream-ordered scratch allocation that frees itself (cudaFreeAsync on the same stream) when it goes out of scope.
+struct Scratch {
+  void* p = nullptr;
+  cudaStream_t s = nullptr;
+  Scratch() = default;
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+  int alloc(size_t bytes, cudaStream_t stream)
+  {
+    release();
+    s = stream;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      fprintf(stderr, "[icicle_b200] cudaMallocAsync(%zu) failed: %s\n", bytes, cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return map_alloc_error(e);
+    }
+    return B200_SUCCESS;
+  }
+  void release()
+  {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+  }
+  ~Scratch() { release(); }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Input staging: returns a device pointer for `src`; copies through `buf` if `src` is host memory.
+static inline int stage_in(const void*& dev_ptr, const void* src, size_t bytes, bool on_device, cudaStream_t s, Scratch& buf)
+{
+  if (on_device) {
+    dev_ptr = src;
+    return B200_SUCCESS;
+  }
+  int err = buf.alloc(bytes, s);
+  if (err) return err;
+  B200_CUDA_TRY(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, s), B200_COPY_FAILED);
+  dev_ptr = buf.p;
+  return B200_SUCCESS;
+}
+// Output staging: a device pointer to write results into (the user's if on device, scratch otherwise).
+static inline int stage_out(void*& dev_ptr, void* dst, size_t bytes, bool on_device, cudaStream_t s, Scratch& buf)
+{
+  if (on_device) {
+    dev_ptr = dst;
+    return B200_SUCCESS;
+  }
+  int err = buf.alloc(bytes, s);
+  if (err) return err;
+  dev_ptr = buf.p;
+  return B200_SUCCESS;
+}
+// Finish: copy results back if they live on the host; block unless (async and results on device).
+// Matches the reference contract "results to host force a sync even if is_async" (icicle/include/icicle/msm.h:45-51).
+static inline int finish_out(void* dst, const void* dev_ptr, size_t bytes, bool on_device, bool is_async, cudaStream_t s)
+{
+  if (!on_device) {
+    B200_CUDA_TRY(cudaMemcpyAsync(dst, dev_ptr, bytes, cudaMemcpyDeviceToHost, s), B200_COPY_FAILED);
+    B200_CUDA_TRY(cudaStreamSynchronize(s), B200_SYNCHRONIZATION_FAILED);
+  } else if (!is_async) {
+    B200_CUDA_TRY(cudaStreamSynchronize(s), B200_SYNCHRONIZATION_FAILED);
+  }
+  return B200_SUCCESS;
+}
+
+static inline int num_sms()
+{
+  static thread_local int cached_dev = -1, cached = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// ---- field dispatch -------------------------------------------------------------------------------------------------
+#define B200_FIELD_CASE(ID, PARAMS, ...)                                                                               \
+  case ID: {                                                                                                           \
+    using F = ::b200::Fp<::b200::params::PARAMS>;                                                                      \
+    __VA_ARGS__;                                                                                                       \
+  } break;
+
+#define B200_DISPATCH_FIELD(field, ...)                                                                                \
+  switch (field) {                                                                                                     \
+    B200_FIELD_CASE(B200_FIELD_BN254_FR, bn254_fr, __VA_ARGS__)                                                        \
+    B200_FIELD_CASE(B200_FIELD_BN254_FQ, bn254_fq, __VA_ARGS__)                                                        \
+    B200_FIELD_CASE(B200_FIELD_BLS12_381_FR, bls12_381_fr, __VA_ARGS__)                                                \
+    B200_FIELD_CASE(B200_FIELD_BLS12_381_FQ, bls12_381_fq, __VA_ARGS__)                                                \
+    B200_FIELD_CASE(B200_FIELD_BLS12_377_FR, bls12_377_fr, __VA_ARGS__)                                                \
+    B200_FIELD_CASE(B200_FIELD_BLS12_377_FQ, bls12_377_fq, __VA_ARGS__)                                                \
+    B200_FIELD_CASE(B200_FIELD_BW6_761_FQ, bw6_761_fq, __VA_ARGS__)                                                    \
+    B200_FIELD_CASE(B200_FIELD_STARK252, stark252, __VA_ARGS__)                                                        \
+    B200_FIELD_CASE(B200_FIELD_BABYBEAR, babybear, __VA_ARGS__)                                                        \
+    B200_FIELD_CASE(B200_FIELD_KOALABEAR, koalabear, __VA_ARGS__)                                                      \
+  default:                                                                                                             \
+    return B200_INVALID_ARGUMENT;                                                                                      \
+  }
+
+// fields that have an NTT in the reference (2-adic roots of unity published: icicle/cmake/features.cmake:4-19)
+#define B200_DISPATCH_NTT_FIELD(field, ...)                                                                            \
+  switch (field) {                                                                                                     \
+    B200_FIELD_CASE(B200_FIELD_BN254_FR, bn254_fr, __VA_ARGS__)                                                        \
+    B200_FIELD_CASE(B200_FIELD_BLS12_381_FR, bls12_381_fr, __VA_ARGS__)                                                \
+    B200_FIELD_CASE(B200_FIELD_BLS12_377_FR, bls12_377_fr, __VA_ARGS__)                                                \
+    B200_FIELD_CASE(B200_FIELD_BLS12_377_FQ, bls12_377_fq, __VA_ARGS__)                                                \
+    B200_FIELD_CASE(B200_FIELD_STARK252, stark252, __VA_ARGS__)                                                        \
+    B200_FIELD_CASE(B200_FIELD_BABYBEAR, babybear, __VA_ARGS__)                                                        \
+    B200_FIELD_CASE(B200_FIELD_KOALABEAR, koalabear, __VA_ARGS__)                                                      \
+  default:                                                                                                             \
+    return B200_API_NOT_IMPLEMENTED;                                                                                   \
+  }
+
+static inline int field_limbs(int field)
+{
+  switch (field) {
+  case B200_FIELD_BN254_FR: case B200_FIELD_BN254_FQ: case B200_FIELD_BLS12_381_FR: case B200_FIELD_BLS12_377_FR:
+  case B200_FIELD_STARK252: return 8;
+  case B200_FIELD_BLS12_381_FQ: case B200_FIELD_BLS12_377_FQ: return 12;
+  case B200_FIELD_BW6_761_FQ: return 24;
+  case B200_FIELD_BABYBEAR: case B200_FIELD_KOALABEAR: return 1;
+  default: return 0;
+  }
+}
+
+// ---- curve description: scalar field params, base field type ----------------------------------------------------------
+template <class FrParams_, class Base_>
+struct CurveT {
+  typedef FrParams_ FrParams;
+  typedef Fp<FrParams_> Scalar;
+  typedef Base_ Base; // Fp<> for G1, Fp2<> for G2
+};
+
+#define B200_CURVE_CASE(ID, FR, BASE, ...)                                                                             \
+  case ID: {                                                                                                           \
+    using C = ::b200::CurveT<::b200::params::FR, BASE>;                                                                \
+    __VA_ARGS__;                                                                                                       \
+  } break;
+
+#define B200_DISPATCH_CURVE(curve, ...)                                                                                \
+  switch (curve) {                                                                                                     \
+    B200_CURVE_CASE(B200_CURVE_BN254_G1, bn254_fr, ::b200::Fp<::b200::params::bn254_fq>, __VA_ARGS__)                  \
+    B200_CURVE_CASE(B200_CURVE_BN254_G2, bn254_fr, ::b200::Fp2<::b200::params::bn254_fq>, __VA_ARGS__)                 \
+    B200_CURVE_CASE(B200_CURVE_BLS12_381_G1, bls12_381_fr, ::b200::Fp<::b200::params::bls12_381_fq>, __VA_ARGS__)      \
+    B200_CURVE_CASE(B200_CURVE_BLS12_381_G2, bls12_381_fr, ::b200::Fp2<::b200::params::bls12_381_fq>, __VA_ARGS__)     \
+    B200_CURVE_CASE(B200_CURVE_BLS12_377_G1, bls12_377_fr, ::b200::Fp<::b200::params::bls12_377_fq>, __VA_ARGS__)      \
+    B200_CURVE_CASE(B200_CURVE_BLS12_377_G2, bls12_377_fr, ::b200::Fp2<::b200::params::bls12_377_fq>, __VA_ARGS__)     \
+    B200_CURVE_CASE(B200_CURVE_BW6_761_G1, bls12_377_fq, ::b200::Fp<::b200::params::bw6_761_fq>, __VA_ARGS__)          \
+    B200_CURVE_CASE(B200_CURVE_BW6_761_G2, bls12_377_fq, ::b200::Fp<::b200::params::bw6_761_fq>, __VA_ARGS__)          \
+    B200_CURVE_CASE(B200_CURVE_GRUMPKIN, bn254_fq, ::b200::Fp<::b200::params::bn254_fr>, __VA_ARGS__)                  \
+  default:                                                                                                             \
+    return B200_INVALID_ARGUMENT;                                                                                      \
+  }
+
+} // namespace b200

@@ -1,0 +1,568 @@
+// Multi-scalar multiplication (Pippenger bucket method) for sm_100a.
+//
+// Replaces (reference, CPU): cpu_msm / Msm::run_msm (icicle/backend/cpu/src/curve/cpu_msm.hpp:430-442, 61-75):
+//   phase 1  worker_run_phase1           cpu_msm.hpp:259-314   signed-digit windows + bucket accumulation
+//   phase 2  worker_collapse_segment     cpu_msm.hpp:317-362   running-sum ("line"/"triangle") bucket reduction
+//   phase 3  phase3_final_accumulator    cpu_msm.hpp:365-417   Horner over bucket modules with c doublings
+//   and cpu_msm_precompute_bases         cpu_msm.hpp:454-481
+// Semantics kept: result[b] = sum_i s[b][i] * P[i]; scalars taken mod 2^bitsize when bitsize != 0; optional Montgomery
+// inputs; affine zero (0,0) bases skipped (cpu_msm.hpp:282); batch with shared / per-MSM bases (cpu_msm.hpp:436-437);
+// precompute_factor bases laid out as out[pf*i + j] = 2^(j*shift) * P_i (cpu_msm.hpp:468-478, shift derived from our c).
+// Output is the reference's homogeneous projective point in standard form; the reference compares group elements,
+// not representatives (projective.h:228-231).
+//
+// GPU schedule (one pass over the scalars, one gather pass over the points):
+//   K6  k_digits        scalar -> signed c-bit digits; emits (bucket key, point index|sign) per (scalar, window)
+//   K7  radix sort      (cub::DeviceRadixSort, library) groups entries by bucket
+//   K8  k_accumulate    each thread owns a fixed SLICE of the sorted entry list and sums runs of equal keys with
+//                       mixed XYZZ adds (8M+2S, Montgomery chains in registers); complete runs go straight to the
+//                       bucket, runs cut by a slice boundary become partials -> perfectly balanced for any scalar
+//                       distribution (no large-bucket special case)
+//       k_resolve       stitches the partials of runs that span slices
+//   K9  k_bucket_chunks per-chunk running sums: sum_k (k+1)*B_k = triangle + offset*line
+//       k_sum_groups    tree-sum of chunk results per bucket module
+//   K10 k_final         Horner over bucket modules (c doublings each), XYZZ -> projective, out of Montgomery form
+// The bucket accumulation is integer-multiply bound (about 10 Montgomery products = 1400 IMAD.WIDE per point-window);
+// algorithmic HBM bytes are only |scalar| + |affine| per point (96 B for BN254 G1).
+#pragma once
+#include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cstring>
+#include <algorithm>
+
+namespace b200 { namespace msm {
+
+constexpr int MSM_THREADS = 128;
+constexpr uint32_t SIGN_BIT = 0x80000000u;
+
+template <class F>
+struct alignas(16) AffineRaw {
+  uint32_t w[2 * F::N];
+};
+
+template <class F>
+B200_D Affine<F> load_affine(const uint32_t* p)
+{
+  return {load_el<F>(p), load_el<F>(p + F::N)};
+}
+template <class F>
+B200_D XYZZ<F> load_xyzz(const uint32_t* p)
+{
+  return {load_el<F>(p), load_el<F>(p + F::N), load_el<F>(p + 2 * F::N), load_el<F>(p + 3 * F::N)};
+}
+template <class F>
+B200_D void store_xyzz(uint32_t* p, const XYZZ<F>& a)
+{
+  store_el(p, a.x);
+  store_el(p + F::N, a.y);
+  store_el(p + 2 * F::N, a.zz);
+  store_el(p + 3 * F::N, a.zzz);
+}
+
+struct MsmPlan {
+  int c;              // window bits
+  int bits;           // scalar bits considered
+  int nwin;           // number of c-bit windows covering bits+1
+  int pf;             // precompute factor
+  int nbm;            // bucket modules = ceil(nwin / pf)
+  uint32_t bm_buckets; // buckets per module = 2^(c-1)
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K6: digits.  Thread per scalar.  keys/vals are laid out [batch_local][window][i] so writes are coalesced.
+// key = (batch_local*nbm + bm) * 2^(c-1) + (|d|-1);  d == 0 -> sentinel (total_buckets).  val = point index | sign.
+// ---------------------------------------------------------------------------------------------------------------------
+template <class S>
+__global__ void __launch_bounds__(256) k_digits(
+  const uint32_t* __restrict__ scalars, uint32_t n, uint32_t batch_local, MsmPlan pl, bool scalars_mont, bool shared_points,
+  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t sentinel)
+{
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (uint64_t)n * batch_local) return;
+  const uint32_t b = (uint32_t)(g / n), i = (uint32_t)(g % n);
+  S s = load_fp<S>(scalars + g * S::N);
+  if (scalars_mont) s = s.from_mont();
+  const uint32_t c = pl.c, half = 1u << (c - 1), full = 1u << c;
+  uint32_t carry = 0;
+  const uint64_t ent_base = (uint64_t)b * pl.nwin * n;
+  const uint32_t pt_base = shared_points ? 0u : b * n * pl.pf;
+  for (int w = 0; w < pl.nwin; w++) {
+    // raw = bits [w*c, w*c + c) of s, clipped to pl.bits
+    const uint32_t lsb = w * c;
+    uint32_t raw = 0;
+    if (lsb < (uint32_t)pl.bits) {
+      const uint32_t limb = lsb >> 5, off = lsb & 31;
+      uint64_t two = s.v[limb];
+      if (limb + 1 < S::N) two |= (uint64_t)s.v[limb + 1] << 32;
+      raw = (uint32_t)(two >> off) & (full - 1);
+      const uint32_t avail = pl.bits - lsb;
+      if (avail < c) raw &= (1u << avail) - 1;
+    }
+    raw += carry;
+    uint32_t mag, neg;
+    if (raw > half) {
+      mag = full - raw;
+      neg = 1;
+      carry = 1;
+    } else {
+      mag = raw;
+      neg = 0;
+      carry = 0;
+    }
+    const uint32_t j = w / pl.nbm, bm = w % pl.nbm;
+    uint32_t key = sentinel;
+    if (mag) key = (b * pl.nbm + bm) * half + (mag - 1);
+    const uint64_t e = ent_base + (uint64_t)w * n + i;
+    keys[e] = key;
+    vals[e] = (pt_base + i * pl.pf + j) | (neg ? SIGN_BIT : 0u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K8: slice accumulation over the sorted entries.
+// partial slot layout: pkey[2*t + {0,1}] (0xffffffff = empty), pflag bit0 = run starts in this slice, bit1 = run ends here.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t P_EMPTY = 0xffffffffu;
+
+template <class F>
+__global__ void __launch_bounds__(MSM_THREADS) k_accumulate(
+  const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n_entries, uint32_t slice, uint32_t sentinel,
+  const uint32_t* __restrict__ points, uint32_t* __restrict__ buckets, uint32_t* __restrict__ pkey, uint32_t* __restrict__ pflag,
+  uint32_t* __restrict__ ppt, uint64_t n_slices)
+{
+  constexpr int AW = 2 * F::N, XW = 4 * F::N;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_slices) return;
+  const uint64_t beg = t * slice;
+  const uint64_t end = (beg + slice < n_entries) ? beg + slice : n_entries;
+  pkey[2 * t] = P_EMPTY;
+  pkey[2 * t + 1] = P_EMPTY;
+
+  uint32_t cur = keys[beg];
+  if (cur == sentinel) return;
+  bool run_starts_here = (beg == 0) || (keys[beg - 1] != cur);
+  int slot = 0; // head partial goes to slot 0, tail partial to slot 1
+  XYZZ<F> acc = XYZZ<F>::inf();
+
+  uint32_t v = vals[beg];
+  Affine<F> nxt = load_affine<F>(points + (uint64_t)(v & ~SIGN_BIT) * AW);
+  bool nxt_neg = (v & SIGN_BIT) != 0;
+
+  for (uint64_t e = beg; e < end; e++) {
+    Affine<F> p = nxt;
+    const bool neg = nxt_neg;
+    uint32_t knext = sentinel;
+    if (e + 1 < n_entries) knext = keys[e + 1];
+    if (e + 1 < end && knext != sentinel) {
+      uint32_t v2 = vals[e + 1];
+      nxt = load_affine<F>(points + (uint64_t)(v2 & ~SIGN_BIT) * AW);
+      nxt_neg = (v2 & SIGN_BIT) != 0;
+    }
+    if (neg) p.y = p.y.neg();
+    acc.add_affine(p);
+
+    const bool last_in_slice = (e + 1 == end);
+    if (knext != cur || last_in_slice) {
+      const bool run_ends_here = (knext != cur);
+      if (run_starts_here && run_ends_here) {
+        store_xyzz<F>(buckets + (uint64_t)cur * XW, acc); // run fully inside this slice: sole owner of the bucket
+      } else {
+        const uint64_t ps = 2 * t + slot;
+        pkey[ps] = cur;
+        pflag[ps] = (run_starts_here ? 1u : 0u) | (run_ends_here ? 2u : 0u);
+        store_xyzz<F>(ppt + ps * XW, acc);
+      }
+      if (last_in_slice || knext == sentinel) return;
+      cur = knext;
+      run_starts_here = true;
+      slot = 1;
+      acc = XYZZ<F>::inf();
+    }
+  }
+}
+
+// Stitch runs that span several slices: the slot that starts a run walks forward until the slot that ends it.
+template <class F>
+__global__ void __launch_bounds__(MSM_THREADS) k_resolve(
+  const uint32_t* __restrict__ pkey, const uint32_t* __restrict__ pflag, const uint32_t* __restrict__ ppt, uint64_t n_slots,
+  uint32_t* __restrict__ buckets)
+{
+  constexpr int XW = 4 * F::N;
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_slots) return;
+  const uint32_t key = pkey[j];
+  if (key == P_EMPTY) return;
+  const uint32_t fl = pflag[j];
+  if (!(fl & 1u)) return; // not the start of a run
+  XYZZ<F> acc = load_xyzz<F>(ppt + j * XW);
+  if (!(fl & 2u)) {
+    for (uint64_t k = j + 1; k < n_slots; k++) {
+      if (pkey[k] == P_EMPTY) continue;
+      XYZZ<F> o = load_xyzz<F>(ppt + k * XW);
+      acc.add(o);
+      if (pflag[k] & 2u) break;
+    }
+  }
+  store_xyzz<F>(buckets + (uint64_t)key * XW, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K9: bucket reduction.  Module m has buckets B_0..B_{nb-1} with weights 1..nb.  Thread (m, g) handles the chunk
+// [g*L, (g+1)*L): tri = sum (k - g*L + 1) B_k, line = sum B_k (descending running sums, cpu_msm.hpp:338-351), and
+// emits tri + (g*L) * line.
+// ---------------------------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(MSM_THREADS) k_bucket_chunks(
+  const uint32_t* __restrict__ buckets, uint32_t n_modules, uint32_t nb_log, uint32_t chunk_log, uint32_t* __restrict__ out)
+{
+  constexpr int XW = 4 * F::N;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t chunks_per_module_log = nb_log - chunk_log;
+  if (t >= ((uint64_t)n_modules << chunks_per_module_log)) return;
+  const uint32_t g = (uint32_t)(t & ((1ull << chunks_per_module_log) - 1));
+  const uint64_t first = t << chunk_log; // global bucket index of the chunk start (modules are contiguous)
+  const uint32_t L = 1u << chunk_log;
+  XYZZ<F> line = XYZZ<F>::inf(), tri = XYZZ<F>::inf();
+  for (int k = (int)L - 1; k >= 0; k--) {
+    XYZZ<F> b = load_xyzz<F>(buckets + (first + k) * XW);
+    line.add(b);
+    tri.add(line);
+  }
+  // tri += (g*L) * line
+  uint32_t off = g << chunk_log;
+  if (off) {
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int bit = 31 - __clz(off); bit >= 0; bit--) {
+      acc = acc.dbl();
+      if ((off >> bit) & 1) acc.add(line);
+    }
+    tri.add(acc);
+  }
+  store_xyzz<F>(out + t * XW, tri);
+}
+
+// out[i] = sum_{j < k} in[i*k + j]
+template <class F>
+__global__ void __launch_bounds__(MSM_THREADS) k_sum_groups(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n_out, uint32_t k)
+{
+  constexpr int XW = 4 * F::N;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  XYZZ<F> acc = load_xyzz<F>(in + i * k * XW);
+  for (uint32_t j = 1; j < k; j++) {
+    XYZZ<F> o = load_xyzz<F>(in + (i * k + j) * XW);
+    acc.add(o);
+  }
+  store_xyzz<F>(out + i * XW, acc);
+}
+
+// K10: per batch element: Horner over modules, then XYZZ -> homogeneous projective, out of Montgomery form.
+template <class F>
+__global__ void k_final(const uint32_t* __restrict__ module_sums, uint32_t nbm, uint32_t c, uint32_t batch, uint32_t* __restrict__ results)
+{
+  constexpr int XW = 4 * F::N;
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  XYZZ<F> acc = load_xyzz<F>(module_sums + ((uint64_t)b * nbm + (nbm - 1)) * XW);
+  for (int m = (int)nbm - 2; m >= 0; m--) {
+    for (uint32_t k = 0; k < c; k++) acc = acc.dbl();
+    XYZZ<F> o = load_xyzz<F>(module_sums + ((uint64_t)b * nbm + m) * XW);
+    acc.add(o);
+  }
+  Projective<F> pr = acc.to_projective();
+  uint32_t* o = results + (uint64_t)b * 3 * F::N;
+  store_el(o, pr.x.from_mont());
+  store_el(o + F::N, pr.y.from_mont());
+  store_el(o + 2 * F::N, pr.z.from_mont());
+}
+
+// coordinate-wise to-Montgomery over a flat array of base-field elements (points -> Montgomery form)
+template <class B>
+__global__ void __launch_bounds__(256) k_to_mont(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    store_fp<B>(out + i * B::N, load_fp<B>(in + i * B::N).to_mont());
+}
+
+template <class F>
+struct base_fp {
+  typedef F type;
+};
+template <class P>
+struct base_fp<Fp2<P>> {
+  typedef Fp<P> type;
+};
+
+// Fermat inversion in the base field / its quadratic extension (set-up / precompute only)
+template <class P>
+__device__ Fp<P> inv_fp(const Fp<P>& a)
+{
+  typedef Fp<P> B;
+  uint32_t e[B::N];
+#pragma unroll
+  for (int i = 0; i < B::N; i++) e[i] = P::p(i);
+  e[0] -= 2;
+  B r = B::one();
+  for (int i = B::N * 32 - 1; i >= 0; i--) {
+    r = r * r;
+    if ((e[i / 32] >> (i % 32)) & 1) r = r * a;
+  }
+  return r;
+}
+template <class P>
+__device__ Fp<P> inv_el(const Fp<P>& a)
+{
+  return inv_fp(a);
+}
+template <class P>
+__device__ Fp2<P> inv_el(const Fp2<P>& a)
+{
+  // 1/(a0 + a1 u) = (a0 - a1 u) / (a0^2 - nr a1^2)
+  typedef Fp<P> B;
+  B n = B::sqr(a.c0) - Fp2<P>::mul_nr(B::sqr(a.c1));
+  B ni = inv_fp(n);
+  return {a.c0 * ni, (a.c1 * ni).neg()};
+}
+
+// precompute: out[pf*i + j] = 2^(j*shift) * in[i] (affine).  Thread per input point.
+template <class F>
+__global__ void __launch_bounds__(MSM_THREADS) k_precompute(
+  const uint32_t* __restrict__ in, uint32_t n, uint32_t pf, uint32_t shift, bool in_mont, bool out_mont, uint32_t* __restrict__ out)
+{
+  constexpr int AW = 2 * F::N;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> p = load_affine<F>(in + i * AW);
+  // copy of the original point, form preserved as given (cpu_msm.hpp:469)
+  store_el(out + (i * pf) * AW, p.x);
+  store_el(out + (i * pf) * AW + F::N, p.y);
+  if (!in_mont) {
+    p.x = p.x.to_mont();
+    p.y = p.y.to_mont();
+  }
+  XYZZ<F> q = XYZZ<F>::from_affine(p);
+  for (uint32_t j = 1; j < pf; j++) {
+    for (uint32_t k = 0; k < shift; k++) q = q.dbl();
+    F x = F::zero(), y = F::zero();
+    if (!q.is_inf()) {
+      F zi = inv_el(q.zzz);        // 1/ZZZ
+      F zi2 = F::sqr(zi);          // ZZ^3 = ZZZ^2  =>  1/ZZ = ZZ^2 / ZZZ^2
+      x = q.x * F::sqr(q.zz) * zi2; // X/ZZ = X*ZZ^2/ZZZ^2
+      y = q.y * zi;                 // Y/ZZZ
+    }
+    if (!out_mont) {
+      x = x.from_mont();
+      y = y.from_mont();
+    }
+    store_el(out + (i * pf + j) * AW, x);
+    store_el(out + (i * pf + j) * AW + F::N, y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+inline int ilog2_ceil(uint64_t x)
+{
+  int l = 0;
+  while ((1ull << l) < x) l++;
+  return l;
+}
+
+inline int auto_c(int msm_size, int bits, int pf)
+{
+  // Cost model (EC adds): n * nwin  (accumulation)  +  ~3 * nbm * 2^(c-1)  (reduction incl. offset scalar-muls),
+  // full adds weighted 1.4x a mixed add.  Evaluated for c in [4, 24].
+  double best = 1e300;
+  int best_c = 8;
+  for (int c = 4; c <= 24; c++) {
+    int nwin = (bits + 1 + c - 1) / c;
+    int nbm = (nwin + pf - 1) / pf;
+    double acc = (double)msm_size * nwin;
+    double red = 1.4 * 3.0 * (double)nbm * (double)(1u << (c - 1));
+    double cost = acc + red;
+    if (cost < best) {
+      best = cost;
+      best_c = c;
+    }
+  }
+  return best_c;
+}
+
+template <class C>
+MsmPlan make_plan(int msm_size, const b200_msm_config* cfg)
+{
+  MsmPlan pl;
+  typedef typename C::Scalar S;
+  pl.bits = (cfg->bitsize > 0 && cfg->bitsize <= S::P::BITS) ? cfg->bitsize : S::P::BITS;
+  pl.pf = cfg->precompute_factor > 0 ? cfg->precompute_factor : 1;
+  pl.c = cfg->c > 0 ? cfg->c : auto_c(msm_size, pl.bits, pl.pf);
+  if (pl.c < 2) pl.c = 2;
+  if (pl.c > 24) pl.c = 24;
+  pl.nwin = (pl.bits + 1 + pl.c - 1) / pl.c;
+  pl.nbm = (pl.nwin + pl.pf - 1) / pl.pf;
+  pl.bm_buckets = 1u << (pl.c - 1);
+  return pl;
+}
+
+template <class C>
+int msm_impl(const void* scalars, const void* bases, int msm_size, const b200_msm_config* cfg, void* results)
+{
+  typedef typename C::Scalar S;
+  typedef typename C::Base F;
+  typedef typename base_fp<F>::type B;
+  constexpr int AW = 2 * F::N, XW = 4 * F::N, PW = 3 * F::N;
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  const int batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
+  if (msm_size <= 0) return B200_INVALID_ARGUMENT;
+  const MsmPlan pl = make_plan<C>(msm_size, cfg);
+  const uint32_t n = (uint32_t)msm_size;
+  const bool shared = cfg->are_points_shared_in_batch || batch == 1;
+  const uint64_t n_points = (uint64_t)n * pl.pf * (shared ? 1 : batch);
+  int err;
+
+  // ---- inputs --------------------------------------------------------------------------------------------------------
+  Scratch s_scal, s_pts, s_pts_m, s_res;
+  const void *d_scal, *d_pts;
+  void* d_res;
+  if ((err = stage_in(d_scal, scalars, (size_t)n * batch * S::BYTES, cfg->are_scalars_on_device, s, s_scal))) return err;
+  if ((err = stage_in(d_pts, bases, (size_t)n_points * AW * 4, cfg->are_points_on_device, s, s_pts))) return err;
+  if ((err = stage_out(d_res, results, (size_t)batch * PW * 4, cfg->are_results_on_device, s, s_res))) return err;
+  const uint32_t* pts_m = (const uint32_t*)d_pts;
+  if (!cfg->are_points_montgomery_form) {
+    uint32_t* dst;
+    if (!cfg->are_points_on_device) {
+      dst = s_pts.as<uint32_t>(); // our own staging copy: convert in place
+    } else {
+      if ((err = s_pts_m.alloc((size_t)n_points * AW * 4, s))) return err;
+      dst = s_pts_m.as<uint32_t>();
+    }
+    const uint64_t ncoord = n_points * 2 * (F::N / B::N);
+    unsigned g = (unsigned)std::min<uint64_t>((ncoord + 255) / 256, (uint64_t)num_sms() * 16);
+    k_to_mont<B><<<g, 256, 0, s>>>((const uint32_t*)d_pts, dst, ncoord);
+    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    pts_m = dst;
+  }
+
+  // ---- batch chunking so that entry counts fit 31 bits and memory stays bounded ----------------------------------------
+  const uint64_t ent_per_msm = (uint64_t)n * pl.nwin;
+  uint64_t max_entries = 1ull << 30;
+  int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)batch, max_entries / std::max<uint64_t>(ent_per_msm, 1)));
+  if (cfg->ext_nof_chunks > 0) chunk = std::max(1, (batch + cfg->ext_nof_chunks - 1) / cfg->ext_nof_chunks);
+  // point indices must fit 31 bits
+  if (!shared) {
+    while (chunk > 1 && (uint64_t)chunk * n * pl.pf >= (1ull << 31)) chunk--;
+  }
+  if ((uint64_t)n * pl.pf >= (1ull << 31) || ent_per_msm >= (1ull << 32)) return B200_INVALID_ARGUMENT;
+
+  const uint64_t max_ent = ent_per_msm * chunk;
+  const uint64_t max_modules = (uint64_t)pl.nbm * chunk;
+  const uint64_t max_buckets = max_modules << (pl.c - 1);
+  if (max_buckets >= 0xfffffff0ull) return B200_INVALID_ARGUMENT;
+
+  // slice length: aim for >= 4 slices per resident thread, between 8 and 128 entries
+  const uint64_t target_threads = (uint64_t)num_sms() * 2048;
+  uint32_t slice = (uint32_t)std::min<uint64_t>(128, std::max<uint64_t>(8, max_ent / target_threads));
+  const uint64_t max_slices = (max_ent + slice - 1) / slice;
+
+  // chunk length for the bucket reduction: >= 64K threads if possible
+  int chunk_log = std::max(0, std::min(7, (pl.c - 1 + ilog2_ceil(max_modules)) - 16));
+  if (chunk_log > pl.c - 1) chunk_log = pl.c - 1;
+  const uint64_t max_chunks = max_buckets >> chunk_log;
+
+  Scratch s_k0, s_k1, s_v0, s_v1, s_cub, s_bkt, s_pkey, s_pflag, s_ppt, s_red0, s_red1;
+  if ((err = s_k0.alloc(max_ent * 4, s))) return err;
+  if ((err = s_k1.alloc(max_ent * 4, s))) return err;
+  if ((err = s_v0.alloc(max_ent * 4, s))) return err;
+  if ((err = s_v1.alloc(max_ent * 4, s))) return err;
+  size_t cub_bytes = 0;
+  {
+    cub::DoubleBuffer<uint32_t> dk(s_k0.as<uint32_t>(), s_k1.as<uint32_t>()), dv(s_v0.as<uint32_t>(), s_v1.as<uint32_t>());
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, dk, dv, (int64_t)max_ent, 0, 32, s);
+  }
+  if ((err = s_cub.alloc(cub_bytes, s))) return err;
+  if ((err = s_bkt.alloc(max_buckets * XW * 4, s))) return err;
+  if ((err = s_pkey.alloc(max_slices * 2 * 4, s))) return err;
+  if ((err = s_pflag.alloc(max_slices * 2 * 4, s))) return err;
+  if ((err = s_ppt.alloc(max_slices * 2 * XW * 4, s))) return err;
+  if ((err = s_red0.alloc(std::max<uint64_t>(max_chunks, 1) * XW * 4, s))) return err;
+  if ((err = s_red1.alloc(std::max<uint64_t>(max_chunks / 2 + 1, 1) * XW * 4, s))) return err;
+
+  for (int b0 = 0; b0 < batch; b0 += chunk) {
+    const int bl = std::min(chunk, batch - b0);
+    const uint64_t n_ent = ent_per_msm * bl;
+    const uint32_t n_modules = (uint32_t)pl.nbm * bl;
+    const uint64_t n_buckets = (uint64_t)n_modules << (pl.c - 1);
+    const uint32_t sentinel = (uint32_t)n_buckets;
+    const uint32_t* sc = (const uint32_t*)d_scal + (uint64_t)b0 * n * S::N;
+    const uint32_t* pts = pts_m + (shared ? 0 : (uint64_t)b0 * n * pl.pf * AW);
+
+    // K6
+    {
+      uint64_t th = (uint64_t)n * bl;
+      k_digits<S><<<(unsigned)((th + 255) / 256), 256, 0, s>>>(
+        sc, n, (uint32_t)bl, pl, cfg->are_scalars_montgomery_form, shared, s_k0.as<uint32_t>(), s_v0.as<uint32_t>(), sentinel);
+      B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    }
+    // K7
+    cub::DoubleBuffer<uint32_t> dk(s_k0.as<uint32_t>(), s_k1.as<uint32_t>()), dv(s_v0.as<uint32_t>(), s_v1.as<uint32_t>());
+    {
+      const int key_bits = std::max(1, ilog2_ceil((uint64_t)sentinel + 1));
+      B200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s_cub.p, cub_bytes, dk, dv, (int64_t)n_ent, 0, key_bits, s), B200_UNKNOWN_ERROR);
+    }
+    // K8
+    B200_CUDA_TRY(cudaMemsetAsync(s_bkt.p, 0, n_buckets * XW * 4, s), B200_UNKNOWN_ERROR);
+    const uint64_t n_slices = (n_ent + slice - 1) / slice;
+    k_accumulate<F><<<(unsigned)((n_slices + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
+      dk.Current(), dv.Current(), n_ent, slice, sentinel, pts, s_bkt.as<uint32_t>(), s_pkey.as<uint32_t>(), s_pflag.as<uint32_t>(),
+      s_ppt.as<uint32_t>(), n_slices);
+    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    k_resolve<F><<<(unsigned)((2 * n_slices + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
+      s_pkey.as<uint32_t>(), s_pflag.as<uint32_t>(), s_ppt.as<uint32_t>(), 2 * n_slices, s_bkt.as<uint32_t>());
+    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    // K9
+    const uint64_t n_chunks = n_buckets >> chunk_log;
+    k_bucket_chunks<F><<<(unsigned)((n_chunks + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
+      s_bkt.as<uint32_t>(), n_modules, (uint32_t)(pl.c - 1), (uint32_t)chunk_log, s_red0.as<uint32_t>());
+    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    uint32_t* cur = s_red0.as<uint32_t>();
+    uint32_t* other = s_red1.as<uint32_t>();
+    uint64_t per_module = 1ull << (pl.c - 1 - chunk_log);
+    while (per_module > 1) {
+      const uint32_t k = (uint32_t)std::min<uint64_t>(per_module, 8);
+      const uint64_t n_out = (uint64_t)n_modules * (per_module / k);
+      k_sum_groups<F><<<(unsigned)((n_out + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(cur, other, n_out, k);
+      B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+      std::swap(cur, other);
+      per_module /= k;
+    }
+    // K10
+    k_final<F><<<(bl + 31) / 32, 32, 0, s>>>(cur, (uint32_t)pl.nbm, (uint32_t)pl.c, (uint32_t)bl, (uint32_t*)d_res + (uint64_t)b0 * PW);
+    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  }
+  return finish_out(results, d_res, (size_t)batch * PW * 4, cfg->are_results_on_device, cfg->is_async, s);
+}
+
+template <class C>
+int precompute_impl(const void* in, int n, const b200_msm_config* cfg, void* out)
+{
+  typedef typename C::Base F;
+  constexpr int AW = 2 * F::N;
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  if (n <= 0) return B200_INVALID_ARGUMENT;
+  const MsmPlan pl = make_plan<C>(n, cfg);
+  const uint32_t shift = (uint32_t)pl.c * pl.nbm;
+  Scratch s_in, s_out;
+  const void* d_in;
+  void* d_out;
+  int err;
+  const size_t bytes_in = (size_t)n * AW * 4, bytes_out = bytes_in * pl.pf;
+  if ((err = stage_in(d_in, in, bytes_in, cfg->are_points_on_device, s, s_in))) return err;
+  if ((err = stage_out(d_out, out, bytes_out, cfg->are_results_on_device, s, s_out))) return err;
+  k_precompute<F><<<(n + MSM_THREADS - 1) / MSM_THREADS, MSM_THREADS, 0, s>>>(
+    (const uint32_t*)d_in, (uint32_t)n, (uint32_t)pl.pf, shift, cfg->are_points_montgomery_form, cfg->are_points_montgomery_form, (uint32_t*)d_out);
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  return finish_out(out, d_out, bytes_out, cfg->are_results_on_device, cfg->is_async, s);
+}
+
+}} // namespace b200::msm

@@ -1,0 +1,41 @@
+// One translation unit per curve group (compiled with -DB200_MSM_CURVE=<b200_curve_t value>) so the heavy templates
+// build in parallel.  The entry points are looked up by icicle_b200/csrc/msm.cu.
+#include "msm_impl.cuh"
+
+#define B200_CAT2(a, b) a##b
+#define B200_CAT(a, b) B200_CAT2(a, b)
+
+namespace b200 { namespace msm {
+template <int ID> struct CurveOf;
+template <> struct CurveOf<B200_CURVE_BN254_G1> { typedef CurveT<params::bn254_fr, Fp<params::bn254_fq>> type; };
+template <> struct CurveOf<B200_CURVE_BN254_G2> { typedef CurveT<params::bn254_fr, Fp2<params::bn254_fq>> type; };
+template <> struct CurveOf<B200_CURVE_BLS12_381_G1> { typedef CurveT<params::bls12_381_fr, Fp<params::bls12_381_fq>> type; };
+template <> struct CurveOf<B200_CURVE_BLS12_381_G2> { typedef CurveT<params::bls12_381_fr, Fp2<params::bls12_381_fq>> type; };
+template <> struct CurveOf<B200_CURVE_BLS12_377_G1> { typedef CurveT<params::bls12_377_fr, Fp<params::bls12_377_fq>> type; };
+template <> struct CurveOf<B200_CURVE_BLS12_377_G2> { typedef CurveT<params::bls12_377_fr, Fp2<params::bls12_377_fq>> type; };
+// bw6-761: G1 and G2 live over the same base field (curves/params/bw6_761.h:15-18) and the XYZZ formulas do not
+// involve the curve constant b, so one instantiation serves both.
+template <> struct CurveOf<B200_CURVE_BW6_761_G1> { typedef CurveT<params::bls12_377_fq, Fp<params::bw6_761_fq>> type; };
+template <> struct CurveOf<B200_CURVE_GRUMPKIN> { typedef CurveT<params::bn254_fq, Fp<params::bn254_fr>> type; };
+}} // namespace b200::msm
+
+using namespace b200;
+using namespace b200::msm;
+typedef CurveOf<B200_MSM_CURVE>::type ThisCurve;
+
+extern "C" {
+__attribute__((visibility("hidden"))) int B200_CAT(b200_msm_entry_, B200_MSM_CURVE)(
+  const void* scalars, const void* bases, int msm_size, const b200_msm_config* cfg, void* results)
+{
+  return msm_impl<ThisCurve>(scalars, bases, msm_size, cfg, results);
+}
+__attribute__((visibility("hidden"))) int B200_CAT(b200_msm_precompute_entry_, B200_MSM_CURVE)(
+  const void* in, int n, const b200_msm_config* cfg, void* out)
+{
+  return precompute_impl<ThisCurve>(in, n, cfg, out);
+}
+__attribute__((visibility("hidden"))) int B200_CAT(b200_msm_plan_c_entry_, B200_MSM_CURVE)(int msm_size, const b200_msm_config* cfg)
+{
+  return make_plan<ThisCurve>(msm_size, cfg).c;
+}
+}

@@ -1,0 +1,496 @@
+// NTT over the 2-adic prime fields: domain management + register-resident radix-2^k decimation-in-frequency passes.
+//
+// Replaces (reference, CPU): cpu_ntt / NttCpu::run (icicle/backend/cpu/include/cpu_ntt_main.h:35-47, ntt_cpu.h:69-232),
+// the Winograd/DIT sub-NTT tasks (ntt_task.h:206-1238), input/output reorders and coset multiply (ntt_cpu.h:246-364,
+// 452-467) and the twiddle domain (cpu_ntt_domain.h:63-110,613-654).  The transform computed is the reference's:
+//   forward  out[k] = sum_i (in[i] * g^i) * w^(i*k)          w = domain_root^(max_size/N)
+//   inverse  out[i] = g^-i * N^-1 * sum_k in[k] * w^(-i*k)
+// with `in` un-bit-reversed first for kRN/kRR and `out` bit-reversed for kNR/kRR (kNM/kMN are treated as kNR/kRN,
+// which the reference allows: ntt.h:31-35).  Results are canonical field elements, so they are bit-identical to the
+// reference's whatever the internal schedule.
+//
+// Design (B200): an N = 2^n transform is split into passes of up to 4 radix-2 stages.  In a pass every thread loads
+// 2^k elements (stride 2^lo) into registers, runs k DIF stages on them and stores them back, so a 2^24 transform is 6
+// round trips through HBM instead of 24.  Data stays in the reference's standard form end to end: twiddles are kept in
+// Montgomery form (w*R) and mont_mul(x, w*R) = x*w, so no conversion passes are needed.  Bit-reversal on input/output
+// is folded into the first pass's loads / last pass's stores (a 32-byte element is exactly one DRAM sector, so
+// gathering or scattering whole elements costs no extra HBM traffic); coset multiply is folded into the first pass
+// (forward) and the N^-1 * g^-i scaling into the last pass (inverse).
+// Algorithmic bytes: 2*|E| per element per transform (one read + one write); this schedule moves ceil(n/4) times that.
+#include "common.cuh"
+#include <cstring>
+#include <mutex>
+
+using namespace b200;
+
+namespace {
+
+constexpr int MAX_DEVICES = 64;
+constexpr int MAX_LOG_DOMAIN = 32;
+
+struct Domain {
+  std::mutex mu;
+  bool valid = false;
+  int max_log = 0;
+  uint32_t* twiddles = nullptr; // 2^max_log elements, Montgomery form: tw[i] = root^i * R
+  uint32_t* aux = nullptr;      // device: [0..MAX_LOG_DOMAIN] inv2 table: aux[k] = 2^-k * R ; then scratch
+  uint32_t root[24];            // standard form copy of the primitive root (host)
+};
+// one domain per (field, device id); the reference keeps one per (process, field) (cpu_ntt_domain.h:18-28,45)
+Domain g_domains[B200_FIELD_COUNT][MAX_DEVICES];
+
+struct PassParams {
+  const uint32_t* tw;
+  const uint32_t* in_mul;    // per logical input index multiplier (forward coset), Montgomery form, or nullptr
+  const uint32_t* out_mul;   // per logical output index multiplier (inverse coset incl. 1/N), or nullptr
+  const uint32_t* out_scale; // single element multiplier on store (1/N), or nullptr
+  uint64_t bstride, estride; // element strides: addr(b, i) = b*bstride + i*estride
+  uint32_t n_log, lo, dom_log, batch;
+  uint8_t inverse, gather_in, scatter_out, columns, first, last;
+};
+
+template <class F>
+__device__ __forceinline__ F pow_dev(F base_m, uint64_t e) // base in Montgomery form; returns base^e in Montgomery form
+{
+  F r = F::one();
+  while (e) {
+    if (e & 1) r = r * base_m;
+    base_m = base_m * base_m;
+    e >>= 1;
+  }
+  return r;
+}
+
+// a^(p-2) for a in Montgomery form (Fermat).  Only used in set-up kernels (coset inverse).
+template <class F>
+__device__ F inv_dev(const F& a_m)
+{
+  uint32_t e[F::N];
+#pragma unroll
+  for (int i = 0; i < F::N; i++) e[i] = F::P::p(i);
+  e[0] -= 2; // p is odd and > 2, no borrow
+  F r = F::one();
+  for (int i = F::N * 32 - 1; i >= 0; i--) {
+    r = r * r;
+    if ((e[i / 32] >> (i % 32)) & 1) r = r * a_m;
+  }
+  return r;
+}
+
+// Set-up kernel (1 thread): info[0] = order log2 of root (or 0xffffffff if not a 2-power root of unity);
+// aux[k] = 2^-k in Montgomery form for k <= MAX_LOG_DOMAIN; pw[j] = root^(2^j) (Montgomery) for j < MAX_LOG_DOMAIN.
+template <class F>
+__global__ void k_domain_setup(const uint32_t* root_std, uint32_t* info, uint32_t* aux, uint32_t* pw)
+{
+  F w = load_fp<F>(root_std).to_mont();
+  F one = F::one();
+  uint32_t order = 0xffffffffu;
+  F x = w;
+  for (int j = 0; j < MAX_LOG_DOMAIN; j++) {
+    store_fp<F>(pw + j * F::N, x);
+    if (order == 0xffffffffu && x == one) order = j;
+    x = x * x;
+  }
+  if (order == 0xffffffffu && x == one) order = MAX_LOG_DOMAIN;
+  info[0] = order;
+  // inv2 table: halve repeatedly
+  F h = one;
+  store_fp<F>(aux, h);
+  for (int k = 1; k <= MAX_LOG_DOMAIN; k++) {
+    // h = h/2 mod p
+    uint32_t carry = 0;
+    if (h.v[0] & 1) {
+      uint64_t c = 0;
+#pragma unroll
+      for (int i = 0; i < F::N; i++) {
+        c += (uint64_t)h.v[i] + F::P::p(i);
+        h.v[i] = (uint32_t)c;
+        c >>= 32;
+      }
+      carry = (uint32_t)c;
+    }
+#pragma unroll
+    for (int i = 0; i < F::N - 1; i++) h.v[i] = (h.v[i] >> 1) | (h.v[i + 1] << 31);
+    h.v[F::N - 1] = (h.v[F::N - 1] >> 1) | (carry << 31);
+    store_fp<F>(aux + k * F::N, h);
+  }
+}
+
+// out[i] = scale * base^i (Montgomery form), i < n.  Each thread produces CHUNK consecutive powers.
+// base given as pw[j] = base^(2^j) (Montgomery), j < 64 entries valid up to n_pw.
+template <class F, int CHUNK>
+__global__ void k_power_table(const uint32_t* pw, const uint32_t* scale_m, uint32_t* out, uint64_t n)
+{
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t i0 = t * CHUNK;
+  if (i0 >= n) return;
+  F acc = scale_m ? load_fp<F>(scale_m) : F::one();
+  uint64_t e = i0;
+  for (int j = 0; e; j++, e >>= 1)
+    if (e & 1) acc = acc * load_fp<F>(pw + j * F::N);
+  F b = load_fp<F>(pw);
+  for (int k = 0; k < CHUNK && i0 + k < n; k++) {
+    store_fp<F>(out + (i0 + k) * F::N, acc);
+    acc = acc * b;
+  }
+}
+
+// pw[j] = g^(2^j) for arbitrary g (standard form in), optionally inverted first; 64 entries.
+template <class F>
+__global__ void k_coset_setup(const uint32_t* g_std, int invert, uint32_t* pw)
+{
+  F g = load_fp<F>(g_std).to_mont();
+  if (invert) g = inv_dev(g);
+  for (int j = 0; j < 40; j++) {
+    store_fp<F>(pw + j * F::N, g);
+    g = g * g;
+  }
+}
+
+template <class F, int LOGR>
+__global__ void __launch_bounds__(128) k_ntt_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassParams p)
+{
+  constexpr int R = 1 << LOGR;
+  const uint32_t n_log = p.n_log, lo = p.lo;
+  const uint64_t per_ntt = 1ull << (n_log - LOGR);
+  const uint64_t total = per_ntt * p.batch;
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  uint64_t b, q;
+  if (p.columns) {
+    b = g % p.batch;
+    q = g / p.batch;
+  } else {
+    q = g & (per_ntt - 1);
+    b = g >> (n_log - LOGR);
+  }
+  const uint64_t low = q & ((1ull << lo) - 1);
+  const uint64_t high = q >> lo;
+  const uint64_t base = (high << (lo + LOGR)) | low;
+  const uint64_t boff = b * p.bstride;
+  const uint32_t rev_shift = 64 - n_log;
+
+  F e[R];
+#pragma unroll
+  for (int m = 0; m < R; m++) {
+    uint64_t pos = base + ((uint64_t)m << lo);
+    uint64_t idx = (p.first && p.gather_in) ? (__brevll(pos) >> rev_shift) : pos;
+    e[m] = load_fp<F>(src + (boff + idx * p.estride) * F::N);
+    if (p.in_mul) e[m] = e[m] * load_fp<F>(p.in_mul + pos * F::N);
+  }
+
+  const uint64_t dom_mask = (1ull << p.dom_log) - 1;
+#pragma unroll
+  for (int t = LOGR - 1; t >= 0; --t) {
+    const uint32_t s = lo + t;
+    const uint32_t sh = p.dom_log - (s + 1);
+    const bool trivial = (s == 0); // twiddle exponent is always 0 in the last stage
+#pragma unroll
+    for (int m = 0; m < R; m++) {
+      if (m & (1 << t)) continue;
+      const int m2 = m | (1 << t);
+      F u = e[m], v = e[m2];
+      e[m] = u + v;
+      F d = u - v;
+      if (!trivial) {
+        uint64_t ex = ((((uint64_t)(m & ((1 << t) - 1))) << lo) | low) << sh;
+        if (p.inverse) ex = (0 - ex) & dom_mask;
+        d = d * load_fp<F>(p.tw + ex * F::N);
+      }
+      e[m2] = d;
+    }
+  }
+
+#pragma unroll
+  for (int m = 0; m < R; m++) {
+    uint64_t pos = base + ((uint64_t)m << lo);
+    uint64_t idx = pos;
+    if (p.last) {
+      uint64_t k = n_log ? (__brevll(pos) >> rev_shift) : 0; // logical output index held at position pos
+      if (p.out_mul) e[m] = e[m] * load_fp<F>(p.out_mul + k * F::N);
+      else if (p.out_scale) e[m] = e[m] * load_fp<F>(p.out_scale);
+      if (p.scatter_out) idx = k;
+    }
+    store_fp<F>(dst + (boff + idx * p.estride) * F::N, e[m]);
+  }
+}
+
+template <class F, int LOGR>
+int launch_pass(const uint32_t* src, uint32_t* dst, const PassParams& p, cudaStream_t s)
+{
+  uint64_t total = (1ull << (p.n_log - LOGR)) * p.batch;
+  unsigned blocks = (unsigned)((total + 127) / 128);
+  k_ntt_pass<F, LOGR><<<blocks, 128, 0, s>>>(src, dst, p);
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  return B200_SUCCESS;
+}
+
+template <class F>
+int launch_pass_r(int logr, const uint32_t* src, uint32_t* dst, const PassParams& p, cudaStream_t s)
+{
+  switch (logr) {
+  case 1: return launch_pass<F, 1>(src, dst, p, s);
+  case 2: return launch_pass<F, 2>(src, dst, p, s);
+  case 3: return launch_pass<F, 3>(src, dst, p, s);
+  case 4: return launch_pass<F, 4>(src, dst, p, s);
+  default: return B200_UNKNOWN_ERROR;
+  }
+}
+
+int get_domain(int field, Domain** out)
+{
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev >= MAX_DEVICES) return B200_INVALID_DEVICE;
+  *out = &g_domains[field][dev];
+  return B200_SUCCESS;
+}
+
+template <class F>
+int init_domain_impl(Domain* d, const void* primitive_root, cudaStream_t s)
+{
+  std::lock_guard<std::mutex> lock(d->mu);
+  if (d->valid) return B200_SUCCESS; // idempotent, like cpu_ntt_domain.h:69
+  Scratch root_d, info_d, pw_d;
+  int err;
+  if ((err = root_d.alloc(F::BYTES, s))) return err;
+  if ((err = info_d.alloc(16, s))) return err;
+  if ((err = pw_d.alloc((size_t)MAX_LOG_DOMAIN * F::BYTES, s))) return err;
+  uint32_t* aux = nullptr;
+  B200_CUDA_TRY(cudaMalloc(&aux, (size_t)(MAX_LOG_DOMAIN + 1) * F::BYTES), B200_ALLOCATION_FAILED);
+  B200_CUDA_TRY(cudaMemcpyAsync(root_d.p, primitive_root, F::BYTES, cudaMemcpyHostToDevice, s), B200_COPY_FAILED);
+  k_domain_setup<F><<<1, 1, 0, s>>>(root_d.as<uint32_t>(), info_d.as<uint32_t>(), aux, pw_d.as<uint32_t>());
+  uint32_t order = 0;
+  B200_CUDA_TRY(cudaMemcpyAsync(&order, info_d.p, 4, cudaMemcpyDeviceToHost, s), B200_COPY_FAILED);
+  B200_CUDA_TRY(cudaStreamSynchronize(s), B200_SYNCHRONIZATION_FAILED);
+  if (order == 0xffffffffu || order > 31) {
+    cudaFree(aux);
+    fprintf(stderr, "[icicle_b200] ntt_init_domain: primitive root is not a 2^k-th root of unity (k <= 31)\n");
+    return B200_INVALID_ARGUMENT; // cpu_ntt_domain.h:91-94
+  }
+  const uint64_t size = 1ull << order;
+  uint32_t* tw = nullptr;
+  cudaError_t ce = cudaMalloc(&tw, size * F::BYTES);
+  if (ce != cudaSuccess) {
+    (void)cudaGetLastError();
+    cudaFree(aux);
+    return map_alloc_error(ce);
+  }
+  constexpr int CHUNK = 64;
+  uint64_t threads = (size + CHUNK - 1) / CHUNK;
+  k_power_table<F, CHUNK><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(pw_d.as<uint32_t>(), nullptr, tw, size);
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  B200_CUDA_TRY(cudaStreamSynchronize(s), B200_SYNCHRONIZATION_FAILED);
+  d->twiddles = tw;
+  d->aux = aux;
+  d->max_log = (int)order;
+  memcpy(d->root, primitive_root, F::BYTES);
+  d->valid = true;
+  return B200_SUCCESS;
+}
+
+// split n_log stages into passes of at most `maxr` stages, as evenly as possible, highest stages first
+int plan_passes(int n_log, int maxr, int* radices)
+{
+  int k = (n_log + maxr - 1) / maxr;
+  int basev = n_log / k, extra = n_log % k;
+  for (int i = 0; i < k; i++) radices[i] = basev + (i < extra ? 1 : 0);
+  return k;
+}
+
+template <class F>
+int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output)
+{
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  if (size <= 0 || (size & (size - 1))) return B200_INVALID_ARGUMENT; // cpu_ntt_main.h:38
+  int n_log = 0;
+  while ((1 << n_log) < size) n_log++;
+  if (!d->valid) {
+    fprintf(stderr, "[icicle_b200] ntt: domain not initialised for this field/device\n");
+    return B200_INVALID_ARGUMENT;
+  }
+  if (n_log > d->max_log) {
+    fprintf(stderr, "[icicle_b200] ntt: size 2^%d exceeds domain 2^%d\n", n_log, d->max_log);
+    return B200_INVALID_ARGUMENT; // cpu_ntt_main.h:39-41
+  }
+  const uint32_t batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
+  const uint64_t total = (uint64_t)size * batch;
+  const size_t bytes = total * F::BYTES;
+  const bool inverse = (dir == B200_NTT_INVERSE);
+  const int ord = cfg->ordering;
+  const bool gather_in = (ord == B200_RN || ord == B200_RR || ord == B200_MN);
+  const bool scatter_out = (ord == B200_NN || ord == B200_RN || ord == B200_MN);
+
+  Scratch sin, sout, stmp, scoset_g, scoset_pw, scoset_tab;
+  const void* din;
+  void* dout;
+  int err;
+  if ((err = stage_in(din, input, bytes, cfg->are_inputs_on_device, s, sin))) return err;
+  if ((err = stage_out(dout, output, bytes, cfg->are_outputs_on_device, s, sout))) return err;
+
+  // ---- coset tables -------------------------------------------------------------------------------------------------
+  bool has_coset = false;
+  if (cfg->coset_gen) {
+    const uint32_t* g = (const uint32_t*)cfg->coset_gen;
+    bool is_one = (g[0] == 1);
+    for (int i = 1; i < F::N; i++) is_one = is_one && (g[i] == 0);
+    has_coset = !is_one;
+  }
+  const uint32_t* in_mul = nullptr;
+  const uint32_t* out_mul = nullptr;
+  const uint32_t* out_scale = nullptr;
+  if (has_coset) {
+    if ((err = scoset_g.alloc(F::BYTES, s))) return err;
+    if ((err = scoset_pw.alloc((size_t)40 * F::BYTES, s))) return err;
+    if ((err = scoset_tab.alloc((size_t)size * F::BYTES, s))) return err;
+    B200_CUDA_TRY(cudaMemcpyAsync(scoset_g.p, cfg->coset_gen, F::BYTES, cudaMemcpyHostToDevice, s), B200_COPY_FAILED);
+    k_coset_setup<F><<<1, 1, 0, s>>>(scoset_g.as<uint32_t>(), inverse ? 1 : 0, scoset_pw.as<uint32_t>());
+    constexpr int CHUNK = 16;
+    uint64_t threads = ((uint64_t)size + CHUNK - 1) / CHUNK;
+    // forward: table[i] = g^i ; inverse: table[i] = N^-1 * g^-i
+    k_power_table<F, CHUNK><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(
+      scoset_pw.as<uint32_t>(), inverse ? d->aux + (size_t)n_log * F::N : nullptr, scoset_tab.as<uint32_t>(), (uint64_t)size);
+    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    if (inverse) out_mul = scoset_tab.as<uint32_t>();
+    else in_mul = scoset_tab.as<uint32_t>();
+  } else if (inverse && n_log > 0) {
+    out_scale = d->aux + (size_t)n_log * F::N;
+  }
+
+  if (n_log == 0) {
+    // N = 1: out = in (coset^0 = 1, N^-1 = 1)
+    if (din != dout) B200_CUDA_TRY(cudaMemcpyAsync(dout, din, bytes, cudaMemcpyDeviceToDevice, s), B200_COPY_FAILED);
+    return finish_out(output, dout, bytes, cfg->are_outputs_on_device, cfg->is_async, s);
+  }
+
+  // ---- pass schedule ---------------------------------------------------------------------------------------------------
+  int maxr = (cfg->ext_ntt_algorithm == B200_NTT_ALG_RADIX2) ? 1 : (F::N >= 12 ? 3 : 4);
+  int radices[32];
+  const int npass = plan_passes(n_log, maxr, radices);
+
+  // working buffer: see the header comment of this file for the in-place rules
+  const bool need_tmp = scatter_out || (gather_in && din == dout) || (npass == 1 && din == dout && (gather_in || scatter_out));
+  uint32_t* work = (uint32_t*)dout;
+  if (need_tmp) {
+    if ((err = stmp.alloc(bytes, s))) return err;
+    work = stmp.as<uint32_t>();
+  }
+
+  PassParams p;
+  memset(&p, 0, sizeof(p));
+  p.tw = d->twiddles;
+  p.n_log = n_log;
+  p.dom_log = d->max_log;
+  p.batch = batch;
+  p.inverse = inverse;
+  p.gather_in = gather_in;
+  p.scatter_out = scatter_out;
+  p.columns = cfg->columns_batch ? 1 : 0;
+  p.bstride = cfg->columns_batch ? 1 : (uint64_t)size;
+  p.estride = cfg->columns_batch ? batch : 1;
+
+  const uint32_t* src = (const uint32_t*)din;
+  int hi = n_log;
+  for (int i = 0; i < npass; i++) {
+    const int r = radices[i];
+    p.lo = hi - r;
+    p.first = (i == 0);
+    p.last = (i == npass - 1);
+    p.in_mul = p.first ? in_mul : nullptr;
+    p.out_mul = p.last ? out_mul : nullptr;
+    p.out_scale = p.last ? out_scale : nullptr;
+    uint32_t* dstp;
+    if (npass == 1) {
+      if (din == dout && (gather_in || scatter_out)) {
+        // single pass, in place, permuting: go through the temporary
+        B200_CUDA_TRY(cudaMemcpyAsync(work, din, bytes, cudaMemcpyDeviceToDevice, s), B200_COPY_FAILED);
+        src = work;
+      }
+      dstp = (uint32_t*)dout;
+    } else if (p.last) {
+      dstp = (uint32_t*)dout;
+    } else {
+      dstp = work;
+    }
+    if ((err = launch_pass_r<F>(r, src, dstp, p, s))) return err;
+    src = dstp;
+    hi -= r;
+  }
+  return finish_out(output, dout, bytes, cfg->are_outputs_on_device, cfg->is_async, s);
+}
+
+} // namespace
+
+extern "C" {
+
+void b200_ntt_default_config(b200_ntt_config* cfg)
+{
+  // default_ntt_config(): icicle/include/icicle/ntt.h:73-86
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->batch_size = 1;
+  cfg->ordering = B200_NN;
+}
+
+int b200_ntt_init_domain(int field, const void* primitive_root, void* stream)
+{
+  if (!primitive_root) return B200_INVALID_POINTER;
+  if (field < 0 || field >= B200_FIELD_COUNT) return B200_INVALID_ARGUMENT;
+  Domain* d;
+  int err = get_domain(field, &d);
+  if (err) return err;
+  B200_DISPATCH_NTT_FIELD(field, return init_domain_impl<F>(d, primitive_root, (cudaStream_t)stream));
+  return B200_API_NOT_IMPLEMENTED;
+}
+
+int b200_ntt_release_domain(int field)
+{
+  if (field < 0 || field >= B200_FIELD_COUNT) return B200_INVALID_ARGUMENT;
+  Domain* d;
+  int err = get_domain(field, &d);
+  if (err) return err;
+  std::lock_guard<std::mutex> lock(d->mu);
+  if (d->valid) { // cpu_ntt_domain.h:613-628
+    cudaDeviceSynchronize();
+    cudaFree(d->twiddles);
+    cudaFree(d->aux);
+    d->twiddles = nullptr;
+    d->aux = nullptr;
+    d->max_log = 0;
+    d->valid = false;
+  }
+  return B200_SUCCESS;
+}
+
+int b200_ntt_get_root_of_unity_from_domain(int field, uint64_t logn, void* rou_out)
+{
+  if (!rou_out) return B200_INVALID_POINTER;
+  if (field < 0 || field >= B200_FIELD_COUNT) return B200_INVALID_ARGUMENT;
+  Domain* d;
+  int err = get_domain(field, &d);
+  if (err) return err;
+  std::lock_guard<std::mutex> lock(d->mu);
+  if (!d->valid || logn > (uint64_t)d->max_log) return B200_INVALID_ARGUMENT; // cpu_ntt_domain.h:643-654
+  // twiddles[1 << (max_log - logn)], converted back to standard form
+  B200_DISPATCH_NTT_FIELD(field, {
+    const uint32_t* src = d->twiddles + (logn == 0 ? 0 : ((size_t)1 << (d->max_log - logn)) * F::N);
+    uint32_t host_m[F::N];
+    B200_CUDA_TRY(cudaMemcpy(host_m, src, F::BYTES, cudaMemcpyDeviceToHost), B200_COPY_FAILED);
+    // the table is kept in Montgomery form; hand back the reference's standard form
+    b200_vec_ops_config vc;
+    b200_vec_ops_default_config(&vc);
+    return b200_convert_montgomery(field, host_m, 1, 0, &vc, rou_out);
+  });
+  return B200_API_NOT_IMPLEMENTED;
+}
+
+int b200_ntt(int field, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output)
+{
+  if (!cfg || !input || !output) return B200_INVALID_POINTER;
+  if (field < 0 || field >= B200_FIELD_COUNT) return B200_INVALID_ARGUMENT;
+  Domain* d;
+  int err = get_domain(field, &d);
+  if (err) return err;
+  B200_DISPATCH_NTT_FIELD(field, return ntt_impl<F>(d, input, size, dir, cfg, output));
+  return B200_API_NOT_IMPLEMENTED;
+}
+
+} // extern "C"

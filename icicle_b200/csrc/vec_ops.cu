@@ -1,0 +1,331 @@
+// Element-wise field vector ops, Montgomery conversion and data-movement ops around the MSM/NTT path.
+// Replaces icicle/backend/cpu/src/field/cpu_vec_ops.cpp:306-341 (op drivers), :354-533 (add/sub/mul/accumulate/scalar ops,
+// convert_montgomery), :535-596 (bit_reverse, slice), cpu_matrix_ops.cpp (transpose) and
+// icicle/backend/cpu/src/curve/cpu_mont_conversion.cpp:11-27.
+//
+// These kernels are HBM-bound streams: one thread per element, 128-bit loads/stores (ld/st.global.v4 on the N%4==0
+// fields), grid sized as a multiple of the SM count with a grid-stride loop.  Algorithmic bytes: 3*|S| per element for
+// the binary ops, 2*|S| for the unary ones.
+#include "common.cuh"
+#include <cstring>
+
+using namespace b200;
+
+namespace {
+
+constexpr int VEC_THREADS = 256;
+
+inline unsigned grid_for(uint64_t n)
+{
+  uint64_t blocks = (n + VEC_THREADS - 1) / VEC_THREADS;
+  uint64_t cap = (uint64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  return (unsigned)blocks;
+}
+
+template <class F, int OP>
+__global__ void __launch_bounds__(VEC_THREADS) k_vec2(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, uint32_t* out, uint64_t n)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    F x = load_fp<F>(a + i * F::N);
+    F y = load_fp<F>(b + i * F::N);
+    F r;
+    if (OP == B200_VEC_ADD || OP == B200_VEC_ACCUMULATE) r = x + y;
+    else if (OP == B200_VEC_SUB) r = x - y;
+    else r = (x * y) * F::r2(); // x*y/R, then *R^2/R  => x*y in standard form
+    store_fp<F>(out + i * F::N, r);
+  }
+}
+
+// out[b][i] = scalar[b] (op) vec[b][i]; element (b,i) lives at b*size + i (rows) or i*batch + b (columns)
+template <class F, int OP>
+__global__ void __launch_bounds__(VEC_THREADS)
+k_scalar_vec(const uint32_t* __restrict__ scalars, const uint32_t* __restrict__ v, uint32_t* out, uint64_t size, uint32_t batch, bool columns)
+{
+  uint64_t total = size * batch;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t bidx = columns ? (t % batch) : (t / size);
+    F s = load_fp<F>(scalars + bidx * F::N);
+    F y = load_fp<F>(v + t * F::N);
+    F r;
+    if (OP == B200_SCALAR_ADD_VEC) r = s + y;
+    else if (OP == B200_SCALAR_SUB_VEC) r = s - y;
+    else r = (s * y) * F::r2();
+    store_fp<F>(out + t * F::N, r);
+  }
+}
+
+template <class F, bool INTO>
+__global__ void __launch_bounds__(VEC_THREADS) k_convert_mont(const uint32_t* __restrict__ in, uint32_t* out, uint64_t n)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    F x = load_fp<F>(in + i * F::N);
+    store_fp<F>(out + i * F::N, INTO ? x.to_mont() : x.from_mont());
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(VEC_THREADS)
+k_bit_reverse(const uint32_t* __restrict__ in, uint32_t* out, uint64_t size, uint32_t logn, uint32_t batch, bool columns)
+{
+  uint64_t total = size * batch;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t b = columns ? (t % batch) : (t / size);
+    uint64_t i = columns ? (t / batch) : (t % size);
+    uint64_t r = logn ? (__brevll(i) >> (64 - logn)) : 0;
+    uint64_t src = columns ? (r * batch + b) : (b * size + r);
+    store_fp<F>(out + t * F::N, load_fp<F>(in + src * F::N));
+  }
+}
+
+// tiled transpose through shared memory, 32x32 elements per tile, element = F::N words
+template <int NW>
+__global__ void __launch_bounds__(256) k_transpose(const uint32_t* __restrict__ in, uint32_t* out, uint32_t rows, uint32_t cols)
+{
+  // one tile = 32 x 32 elements; words of an element are handled by the z-loop to keep the tile in 4 KiB + pad
+  __shared__ uint32_t tile[32][33];
+  uint32_t bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
+  const uint64_t matsz = (uint64_t)rows * cols;
+  const uint32_t* src = in + (uint64_t)blockIdx.z * matsz * NW;
+  uint32_t* dst = out + (uint64_t)blockIdx.z * matsz * NW;
+  for (int w = 0; w < NW; w++) {
+    for (uint32_t j = ty; j < 32; j += 8) {
+      uint32_t r = by + j, c = bx + tx;
+      if (r < rows && c < cols) tile[j][tx] = src[((uint64_t)r * cols + c) * NW + w];
+    }
+    __syncthreads();
+    for (uint32_t j = ty; j < 32; j += 8) {
+      uint32_t c = bx + j, r = by + tx; // output row = c, output col = r
+      if (r < rows && c < cols) dst[((uint64_t)c * rows + r) * NW + w] = tile[tx][j];
+    }
+    __syncthreads();
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(VEC_THREADS) k_slice(
+  const uint32_t* __restrict__ in, uint32_t* out, uint64_t offset, uint64_t stride, uint64_t size_in, uint64_t size_out, uint32_t batch,
+  bool columns)
+{
+  uint64_t total = size_out * batch;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t b = columns ? (t % batch) : (t / size_out);
+    uint64_t i = columns ? (t / batch) : (t % size_out);
+    uint64_t s = offset + i * stride;
+    uint64_t src = columns ? (s * batch + b) : (b * size_in + s);
+    store_fp<F>(out + t * F::N, load_fp<F>(in + src * F::N));
+  }
+}
+
+template <class F>
+int vec_op_impl(int op, const void* a, const void* b, uint64_t size, const b200_vec_ops_config* cfg, void* out)
+{
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  const uint32_t batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
+  const uint64_t n = size * batch;
+  const size_t bytes = n * F::BYTES;
+  const bool scalar_op = (op == B200_SCALAR_ADD_VEC || op == B200_SCALAR_SUB_VEC || op == B200_SCALAR_MUL_VEC);
+  if (n == 0) return B200_SUCCESS;
+  Scratch sa, sb, so;
+  const void *da, *db;
+  void* dout;
+  int err;
+  if ((err = stage_in(da, a, scalar_op ? (size_t)batch * F::BYTES : bytes, cfg->is_a_on_device, s, sa))) return err;
+  if ((err = stage_in(db, b, bytes, cfg->is_b_on_device, s, sb))) return err;
+  void* user_out = (op == B200_VEC_ACCUMULATE) ? const_cast<void*>(a) : out;
+  bool out_on_device = (op == B200_VEC_ACCUMULATE) ? (bool)cfg->is_a_on_device : (bool)cfg->is_result_on_device;
+  if (op == B200_VEC_ACCUMULATE && !out_on_device) {
+    dout = sa.p; // accumulate in the staged copy of a, then copy back
+  } else if ((err = stage_out(dout, user_out, bytes, out_on_device, s, so))) {
+    return err;
+  }
+  const uint32_t* pa = (const uint32_t*)da;
+  const uint32_t* pb = (const uint32_t*)db;
+  uint32_t* po = (uint32_t*)dout;
+  unsigned g = grid_for(n);
+  switch (op) {
+  case B200_VEC_ADD: k_vec2<F, B200_VEC_ADD><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, n); break;
+  case B200_VEC_ACCUMULATE: k_vec2<F, B200_VEC_ADD><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, n); break;
+  case B200_VEC_SUB: k_vec2<F, B200_VEC_SUB><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, n); break;
+  case B200_VEC_MUL: k_vec2<F, B200_VEC_MUL><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, n); break;
+  case B200_SCALAR_ADD_VEC: k_scalar_vec<F, B200_SCALAR_ADD_VEC><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, size, batch, cfg->columns_batch); break;
+  case B200_SCALAR_SUB_VEC: k_scalar_vec<F, B200_SCALAR_SUB_VEC><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, size, batch, cfg->columns_batch); break;
+  case B200_SCALAR_MUL_VEC: k_scalar_vec<F, B200_SCALAR_MUL_VEC><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, size, batch, cfg->columns_batch); break;
+  default: return B200_INVALID_ARGUMENT;
+  }
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  return finish_out(user_out, dout, bytes, out_on_device, cfg->is_async, s);
+}
+
+template <class F>
+int convert_mont_impl(const void* in, uint64_t n, int is_into, const b200_vec_ops_config* cfg, void* out)
+{
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  if (n == 0) return B200_SUCCESS;
+  const size_t bytes = n * F::BYTES;
+  Scratch si, so;
+  const void* din;
+  void* dout;
+  int err;
+  if ((err = stage_in(din, in, bytes, cfg->is_a_on_device, s, si))) return err;
+  if ((err = stage_out(dout, out, bytes, cfg->is_result_on_device, s, so))) return err;
+  unsigned g = grid_for(n);
+  if (is_into) k_convert_mont<F, true><<<g, VEC_THREADS, 0, s>>>((const uint32_t*)din, (uint32_t*)dout, n);
+  else k_convert_mont<F, false><<<g, VEC_THREADS, 0, s>>>((const uint32_t*)din, (uint32_t*)dout, n);
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  return finish_out(out, dout, bytes, cfg->is_result_on_device, cfg->is_async, s);
+}
+
+int curve_base_field(int curve, int* coords_per_point_factor)
+{
+  *coords_per_point_factor = 1;
+  switch (curve) {
+  case B200_CURVE_BN254_G2: *coords_per_point_factor = 2;
+  case B200_CURVE_BN254_G1: return B200_FIELD_BN254_FQ;
+  case B200_CURVE_BLS12_381_G2: *coords_per_point_factor = 2;
+  case B200_CURVE_BLS12_381_G1: return B200_FIELD_BLS12_381_FQ;
+  case B200_CURVE_BLS12_377_G2: *coords_per_point_factor = 2;
+  case B200_CURVE_BLS12_377_G1: return B200_FIELD_BLS12_377_FQ;
+  case B200_CURVE_BW6_761_G1: case B200_CURVE_BW6_761_G2: return B200_FIELD_BW6_761_FQ;
+  case B200_CURVE_GRUMPKIN: return B200_FIELD_BN254_FR;
+  default: return -1;
+  }
+}
+
+} // namespace
+
+extern "C" {
+
+void b200_vec_ops_default_config(b200_vec_ops_config* cfg)
+{
+  // default_vec_ops_config(): icicle/include/icicle/vec_ops.h:19-44
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->batch_size = 1;
+}
+
+int b200_vec_op(int field, int op, const void* a, const void* b, uint64_t size, const b200_vec_ops_config* cfg, void* out)
+{
+  if (!cfg || !a || !b) return B200_INVALID_POINTER;
+  B200_DISPATCH_FIELD(field, return vec_op_impl<F>(op, a, b, size, cfg, out));
+  return B200_INVALID_ARGUMENT;
+}
+
+int b200_convert_montgomery(int field, const void* in, uint64_t size, int is_into, const b200_vec_ops_config* cfg, void* out)
+{
+  if (!cfg || !in || !out) return B200_INVALID_POINTER;
+  const uint64_t n = size * (cfg->batch_size > 0 ? cfg->batch_size : 1);
+  B200_DISPATCH_FIELD(field, return convert_mont_impl<F>(in, n, is_into, cfg, out));
+  return B200_INVALID_ARGUMENT;
+}
+
+int b200_affine_convert_montgomery(int curve, const void* in, uint64_t n, int is_into, const b200_vec_ops_config* cfg, void* out)
+{
+  if (!cfg || !in || !out) return B200_INVALID_POINTER;
+  int k;
+  int field = curve_base_field(curve, &k);
+  if (field < 0) return B200_INVALID_ARGUMENT;
+  const uint64_t coords = n * 2 * k;
+  B200_DISPATCH_FIELD(field, return convert_mont_impl<F>(in, coords, is_into, cfg, out));
+  return B200_INVALID_ARGUMENT;
+}
+
+int b200_projective_convert_montgomery(int curve, const void* in, uint64_t n, int is_into, const b200_vec_ops_config* cfg, void* out)
+{
+  if (!cfg || !in || !out) return B200_INVALID_POINTER;
+  int k;
+  int field = curve_base_field(curve, &k);
+  if (field < 0) return B200_INVALID_ARGUMENT;
+  const uint64_t coords = n * 3 * k;
+  B200_DISPATCH_FIELD(field, return convert_mont_impl<F>(in, coords, is_into, cfg, out));
+  return B200_INVALID_ARGUMENT;
+}
+
+int b200_bit_reverse(int field, const void* in, uint64_t size, const b200_vec_ops_config* cfg, void* out)
+{
+  if (!cfg || !in || !out) return B200_INVALID_POINTER;
+  if (size == 0 || (size & (size - 1))) return B200_INVALID_ARGUMENT; // cpu_vec_ops.cpp:539-542
+  uint32_t logn = 0;
+  while ((1ull << logn) < size) logn++;
+  const uint32_t batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  B200_DISPATCH_FIELD(field, {
+    const size_t bytes = size * batch * F::BYTES;
+    Scratch si, so, stmp;
+    const void* din;
+    void* dout;
+    int err;
+    if ((err = stage_in(din, in, bytes, cfg->is_a_on_device, s, si))) return err;
+    if ((err = stage_out(dout, out, bytes, cfg->is_result_on_device, s, so))) return err;
+    void* target = dout;
+    if (din == dout) { // in-place on device: permute through a temporary
+      if ((err = stmp.alloc(bytes, s))) return err;
+      target = stmp.p;
+    }
+    k_bit_reverse<F><<<grid_for(size * batch), VEC_THREADS, 0, s>>>((const uint32_t*)din, (uint32_t*)target, size, logn, batch, cfg->columns_batch);
+    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    if (target != dout) B200_CUDA_TRY(cudaMemcpyAsync(dout, target, bytes, cudaMemcpyDeviceToDevice, s), B200_COPY_FAILED);
+    return finish_out(out, dout, bytes, cfg->is_result_on_device, cfg->is_async, s);
+  });
+  return B200_INVALID_ARGUMENT;
+}
+
+int b200_matrix_transpose(int field, const void* in, uint32_t rows, uint32_t cols, const b200_vec_ops_config* cfg, void* out)
+{
+  if (!cfg || !in || !out) return B200_INVALID_POINTER;
+  if (rows == 0 || cols == 0) return B200_INVALID_ARGUMENT;
+  const uint32_t batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
+  if (cfg->columns_batch && batch > 1) return B200_API_NOT_IMPLEMENTED;
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  const int nw = field_limbs(field);
+  if (nw == 0) return B200_INVALID_ARGUMENT;
+  const size_t bytes = (size_t)rows * cols * batch * nw * 4;
+  Scratch si, so, stmp;
+  const void* din;
+  void* dout;
+  int err;
+  if ((err = stage_in(din, in, bytes, cfg->is_a_on_device, s, si))) return err;
+  if ((err = stage_out(dout, out, bytes, cfg->is_result_on_device, s, so))) return err;
+  void* target = dout;
+  if (din == dout) {
+    if ((err = stmp.alloc(bytes, s))) return err;
+    target = stmp.p;
+  }
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
+  switch (nw) {
+  case 1: k_transpose<1><<<grid, 256, 0, s>>>((const uint32_t*)din, (uint32_t*)target, rows, cols); break;
+  case 8: k_transpose<8><<<grid, 256, 0, s>>>((const uint32_t*)din, (uint32_t*)target, rows, cols); break;
+  case 12: k_transpose<12><<<grid, 256, 0, s>>>((const uint32_t*)din, (uint32_t*)target, rows, cols); break;
+  case 24: k_transpose<24><<<grid, 256, 0, s>>>((const uint32_t*)din, (uint32_t*)target, rows, cols); break;
+  default: return B200_INVALID_ARGUMENT;
+  }
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  if (target != dout) B200_CUDA_TRY(cudaMemcpyAsync(dout, target, bytes, cudaMemcpyDeviceToDevice, s), B200_COPY_FAILED);
+  return finish_out(out, dout, bytes, cfg->is_result_on_device, cfg->is_async, s);
+}
+
+int b200_slice(int field, const void* in, uint64_t offset, uint64_t stride, uint64_t size_in, uint64_t size_out,
+               const b200_vec_ops_config* cfg, void* out)
+{
+  if (!cfg || !in || !out) return B200_INVALID_POINTER;
+  if (size_out == 0) return B200_SUCCESS;
+  if (offset + (size_out - 1) * stride >= size_in) return B200_INVALID_ARGUMENT; // cpu_vec_ops.cpp:592
+  const uint32_t batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  B200_DISPATCH_FIELD(field, {
+    const size_t bytes_in = size_in * batch * F::BYTES, bytes_out = size_out * batch * F::BYTES;
+    Scratch si, so;
+    const void* din;
+    void* dout;
+    int err;
+    if ((err = stage_in(din, in, bytes_in, cfg->is_a_on_device, s, si))) return err;
+    if ((err = stage_out(dout, out, bytes_out, cfg->is_result_on_device, s, so))) return err;
+    k_slice<F><<<grid_for(size_out * batch), VEC_THREADS, 0, s>>>((const uint32_t*)din, (uint32_t*)dout, offset, stride, size_in, size_out, batch, cfg->columns_batch);
+    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    return finish_out(out, dout, bytes_out, cfg->is_result_on_device, cfg->is_async, s);
+  });
+  return B200_INVALID_ARGUMENT;
+}
+
+} // extern "C"

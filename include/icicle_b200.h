@@ -1,0 +1,221 @@
+/*
+ * icicle_b200 -- C ABI of the B200 (sm_100a) MSM / NTT / vec-ops engine.
+ *
+ * This is the drop-in boundary below ICICLE's backend-registration layer: every entry point here is what one of the
+ * reference's per-device backend hooks binds to (the C++ registration shims under icicle_b200/shim/ are one-line
+ * adapters).  Plain pointers and sizes only; no C++ / torch types.  All file:line citations are
+ * relative to the reference tree (ingonyama-zk/icicle @ 625532a6).
+ *
+ * Data conventions (identical to the reference):
+ *   - field element  = N little-endian uint32 limbs, canonical value in [0,p)      icicle/include/icicle/math/storage.h:36-48
+ *   - affine point   = {x, y}, zero is (0,0)                                        icicle/include/icicle/curves/affine.h:11-39
+ *   - projective     = homogeneous {X, Y, Z}, zero is (0,1,0)                       icicle/include/icicle/curves/projective.h:23-31
+ *   - G2 coordinates = {real, imaginary} pairs of base-field elements               icicle/include/icicle/fields/complex_extension.h
+ *   - "Montgomery form" means x*R mod p with R = 2^(32*N)                           icicle/include/icicle/fields/params_gen.h:35-50
+ * Return value: 0 on success, otherwise the numeric value of the reference's eIcicleError
+ * (icicle/include/icicle/errors.h:13-29).
+ */
+#ifndef ICICLE_B200_H
+#define ICICLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes: numeric values of eIcicleError (errors.h:13-29) ---- */
+enum {
+  B200_SUCCESS = 0,
+  B200_INVALID_DEVICE = 1,
+  B200_OUT_OF_MEMORY = 2,
+  B200_INVALID_POINTER = 3,
+  B200_ALLOCATION_FAILED = 4,
+  B200_DEALLOCATION_FAILED = 5,
+  B200_COPY_FAILED = 6,
+  B200_SYNCHRONIZATION_FAILED = 7,
+  B200_STREAM_CREATION_FAILED = 8,
+  B200_STREAM_DESTRUCTION_FAILED = 9,
+  B200_API_NOT_IMPLEMENTED = 10,
+  B200_INVALID_ARGUMENT = 11,
+  B200_UNKNOWN_ERROR = 14
+};
+
+/* ---- fields (scalar / coefficient types).  limbs: bn254/bls/stark252 = 8, *_fq 381/377 = 12, bw6 = 24, bears = 1 ---- */
+typedef enum {
+  B200_FIELD_BN254_FR = 0,     /* bn254::scalar_t,     fields/snark_fields/bn254_scalar.h   (also grumpkin base field) */
+  B200_FIELD_BN254_FQ = 1,     /* bn254 base field,    fields/snark_fields/bn254_base.h     (also grumpkin scalar field) */
+  B200_FIELD_BLS12_381_FR = 2, /* fields/snark_fields/bls12_381_scalar.h */
+  B200_FIELD_BLS12_381_FQ = 3, /* fields/snark_fields/bls12_381_base.h */
+  B200_FIELD_BLS12_377_FR = 4, /* fields/snark_fields/bls12_377_scalar.h */
+  B200_FIELD_BLS12_377_FQ = 5, /* fields/snark_fields/bls12_377_base.h     (also bw6_761 scalar field) */
+  B200_FIELD_BW6_761_FQ = 6,   /* fields/snark_fields/bw6_761_base.h */
+  B200_FIELD_STARK252 = 7,     /* fields/stark_fields/stark252.h */
+  B200_FIELD_BABYBEAR = 8,     /* fields/stark_fields/babybear.h */
+  B200_FIELD_KOALABEAR = 9,    /* fields/stark_fields/koalabear.h */
+  B200_FIELD_COUNT
+} b200_field_t;
+
+/* ---- curve groups for MSM ---- */
+typedef enum {
+  B200_CURVE_BN254_G1 = 0,     /* curves/params/bn254.h */
+  B200_CURVE_BN254_G2 = 1,
+  B200_CURVE_BLS12_381_G1 = 2, /* curves/params/bls12_381.h */
+  B200_CURVE_BLS12_381_G2 = 3,
+  B200_CURVE_BLS12_377_G1 = 4, /* curves/params/bls12_377.h */
+  B200_CURVE_BLS12_377_G2 = 5,
+  B200_CURVE_BW6_761_G1 = 6,   /* curves/params/bw6_761.h (G2 is over the same base field) */
+  B200_CURVE_BW6_761_G2 = 7,
+  B200_CURVE_GRUMPKIN = 8,     /* curves/params/grumpkin.h */
+  B200_CURVE_COUNT
+} b200_curve_t;
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Device runtime -- what our DeviceAPI subclass forwards to (icicle/include/icicle/device_api.h:44-182; model:
+ * icicle/backend/cpu/src/cpu_device_api.cpp).  `stream` is an opaque cudaStream_t (icicleStreamHandle, device_api.h:25).
+ * ---------------------------------------------------------------------------------------------------------------- */
+B200_API int b200_get_device_count(int* count);                    /* DeviceAPI::get_device_count        device_api.h:52  */
+B200_API int b200_set_device(int device_id);                       /* DeviceAPI::set_device              device_api.h:46  */
+B200_API int b200_malloc(void** ptr, size_t bytes);                /* DeviceAPI::allocate_memory         device_api.h:66  */
+B200_API int b200_malloc_async(void** ptr, size_t bytes, void* stream);
+B200_API int b200_free(void* ptr);                                 /* DeviceAPI::free_memory             device_api.h:84  */
+B200_API int b200_free_async(void* ptr, void* stream);
+B200_API int b200_get_available_memory(size_t* total, size_t* free_bytes); /* DeviceAPI::get_available_memory device_api.h:101 */
+B200_API int b200_memset(void* ptr, int value, size_t bytes);      /* DeviceAPI::memset                  device_api.h:111 */
+B200_API int b200_memset_async(void* ptr, int value, size_t bytes, void* stream);
+B200_API int b200_copy_to_device(void* dst, const void* src, size_t bytes, void* stream, int is_async); /* copy / copy_async h2d  device_api.h:131-150 */
+B200_API int b200_copy_to_host(void* dst, const void* src, size_t bytes, void* stream, int is_async);   /* d2h */
+B200_API int b200_copy_device_to_device(void* dst, const void* src, size_t bytes, void* stream, int is_async); /* d2d */
+B200_API int b200_synchronize(void* stream);                       /* DeviceAPI::synchronize (stream==NULL: whole device) device_api.h:158 */
+B200_API int b200_create_stream(void** stream);                    /* DeviceAPI::create_stream           device_api.h:166 */
+B200_API int b200_destroy_stream(void* stream);                    /* DeviceAPI::destroy_stream          device_api.h:173 */
+/* pinned host staging (used by the e2e path and by bench.py; not part of the reference API) */
+B200_API int b200_host_alloc_pinned(void** ptr, size_t bytes);
+B200_API int b200_host_free_pinned(void* ptr);
+/* size in bytes of one element of `field` / one affine or projective point of `curve` */
+B200_API int b200_field_bytes(int field);
+B200_API int b200_curve_scalar_field(int curve);
+B200_API int b200_curve_affine_bytes(int curve);
+B200_API int b200_curve_projective_bytes(int curve);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * MSM -- replaces MsmImpl / MsmPreComputeImpl (icicle/include/icicle/backend/msm_backend.h:11-17,29-34 and the G2
+ * twins :47-53,65-70), i.e. cpu_msm / cpu_msm_precompute_bases (icicle/backend/cpu/src/curve/cpu_msm.hpp:430-481).
+ * Field-for-field mirror of icicle::MSMConfig (icicle/include/icicle/msm.h:21-53) plus the backend extension keys the
+ * closed CUDA backend reads from ConfigExtension (icicle/include/icicle/backend/msm_config.h:10-17), flattened.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  void* stream;
+  int precompute_factor;
+  int c;                       /* 0 = choose automatically */
+  int bitsize;                 /* 0 = scalar field bit size; otherwise scalars are taken mod 2^bitsize (cpu_msm.hpp:203,289) */
+  int batch_size;
+  uint8_t are_points_shared_in_batch;
+  uint8_t are_scalars_on_device;
+  uint8_t are_scalars_montgomery_form;
+  uint8_t are_points_on_device;
+  uint8_t are_points_montgomery_form;
+  uint8_t are_results_on_device;
+  uint8_t is_async;
+  uint8_t reserved;
+  int ext_large_bucket_factor; /* accepted, unused: work is split by fixed-size slices, not per bucket */
+  int ext_nof_chunks;          /* 0 = auto: number of batch chunks processed at a time */
+  int ext_is_big_triangle;     /* accepted, unused */
+} b200_msm_config;
+
+B200_API void b200_msm_default_config(b200_msm_config* cfg);      /* default_msm_config(), msm.h:60-78 */
+/* results[b] = sum_i scalars[b*n+i] * bases[(shared ? 0 : b*n) + i]   (precompute: bases[pf*i + j]) */
+B200_API int b200_msm(int curve, const void* scalars, const void* bases, int msm_size, const b200_msm_config* cfg, void* results);
+/* out[pf*i + j] = 2^(j*shift) * in[i], affine; `shift` depends on (c, bitsize, pf) exactly as b200_msm expects. */
+B200_API int b200_msm_precompute_bases(int curve, const void* input_bases, int nof_bases, const b200_msm_config* cfg, void* output_bases);
+/* window size b200_msm would pick for this problem (exposed for the bench sweep and for tests) */
+B200_API int b200_msm_choose_c(int curve, int msm_size, const b200_msm_config* cfg);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * NTT -- replaces NttImpl / NttInitDomainImpl / NttReleaseDomainImpl / NttGetRouFromDomainImpl
+ * (icicle/include/icicle/backend/ntt_backend.h:13-19,52-53,68,81), i.e. cpu_ntt & CpuNttDomain
+ * (icicle/backend/cpu/include/cpu_ntt_main.h:35-47, cpu_ntt_domain.h:63-110,613-654).
+ * Mirror of icicle::NTTConfig<S> (icicle/include/icicle/ntt.h:52-64); coset_gen is passed by pointer because its size
+ * depends on the field (NULL = one = no coset).
+ * ---------------------------------------------------------------------------------------------------------------- */
+enum { B200_NTT_FORWARD = 0, B200_NTT_INVERSE = 1 };                                   /* NTTDir,  ntt.h:23-26 */
+enum { B200_NN = 0, B200_NR = 1, B200_RN = 2, B200_RR = 3, B200_NM = 4, B200_MN = 5 }; /* Ordering, ntt.h:37-44 */
+enum { B200_NTT_ALG_AUTO = 0, B200_NTT_ALG_RADIX2 = 1, B200_NTT_ALG_MIXED_RADIX = 2 }; /* backend/ntt_config.h:7-18 */
+
+typedef struct {
+  void* stream;
+  const void* coset_gen;       /* standard form, one field element; NULL = no coset */
+  int batch_size;
+  uint8_t columns_batch;
+  uint8_t are_inputs_on_device;
+  uint8_t are_outputs_on_device;
+  uint8_t is_async;
+  int ordering;
+  int ext_ntt_algorithm;       /* CUDA_NTT_ALGORITHM extension key */
+  int ext_fast_twiddles;       /* CUDA_NTT_FAST_TWIDDLES_MODE: accepted, unused */
+} b200_ntt_config;
+
+B200_API void b200_ntt_default_config(b200_ntt_config* cfg);
+/* primitive_root must generate a subgroup of order 2^k; k becomes the domain's max_log_size (cpu_ntt_domain.h:78-94).
+ * Idempotent if a domain already exists for (field, current device) (cpu_ntt_domain.h:69). */
+B200_API int b200_ntt_init_domain(int field, const void* primitive_root, void* stream);
+B200_API int b200_ntt_release_domain(int field);
+B200_API int b200_ntt_get_root_of_unity_from_domain(int field, uint64_t logn, void* rou_out);
+B200_API int b200_ntt(int field, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * vec-ops around the path -- replace the per-op hooks of icicle/include/icicle/backend/vec_ops_backend.h:11-83,85-270,
+ * i.e. icicle/backend/cpu/src/field/cpu_vec_ops.cpp:354-633 and cpu_mont_conversion.cpp:11-27.
+ * Mirror of icicle::VecOpsConfig (icicle/include/icicle/vec_ops.h:19-44).
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  void* stream;
+  uint8_t is_a_on_device;
+  uint8_t is_b_on_device;
+  uint8_t is_result_on_device;
+  uint8_t is_async;
+  int batch_size;
+  uint8_t columns_batch;
+  uint8_t reserved[3];
+} b200_vec_ops_config;
+
+typedef enum {
+  B200_VEC_ADD = 0,        /* vector_add          vec_ops_backend.h:85  */
+  B200_VEC_SUB = 1,        /* vector_sub          */
+  B200_VEC_MUL = 2,        /* vector_mul          */
+  B200_VEC_ACCUMULATE = 3, /* vector_accumulate: a[i] += b[i], result pointer ignored */
+  B200_SCALAR_ADD_VEC = 4, /* scalar_add_vec: out = a[batch] + b */
+  B200_SCALAR_SUB_VEC = 5, /* scalar_sub_vec: out = a[batch] - b */
+  B200_SCALAR_MUL_VEC = 6  /* scalar_mul_vec: out = a[batch] * b */
+} b200_vec_op_t;
+
+B200_API void b200_vec_ops_default_config(b200_vec_ops_config* cfg);
+/* element-wise op over size*batch_size elements (scalar_* ops: `a` holds one scalar per batch, cpu_vec_ops.cpp:325-341) */
+B200_API int b200_vec_op(int field, int op, const void* a, const void* b, uint64_t size, const b200_vec_ops_config* cfg, void* out);
+/* convert_montgomery (vec_ops_backend.h ConvertMontgomery; cpu_vec_ops.cpp) */
+B200_API int b200_convert_montgomery(int field, const void* in, uint64_t size, int is_into, const b200_vec_ops_config* cfg, void* out);
+/* bit_reverse (cpu_vec_ops.cpp:535-575): out[i] = in[bitrev(i)], size must be a power of two */
+B200_API int b200_bit_reverse(int field, const void* in, uint64_t size, const b200_vec_ops_config* cfg, void* out);
+/* matrix_transpose (vec_ops_backend.h:204-212; cpu_matrix_ops.cpp): out[c*rows + r] = in[r*cols + c] */
+B200_API int b200_matrix_transpose(int field, const void* in, uint32_t rows, uint32_t cols, const b200_vec_ops_config* cfg, void* out);
+/* slice (cpu_vec_ops.cpp:577-596): out[i] = in[offset + i*stride] */
+B200_API int b200_slice(int field, const void* in, uint64_t offset, uint64_t stride, uint64_t size_in, uint64_t size_out,
+               const b200_vec_ops_config* cfg, void* out);
+/* curve Montgomery conversion (icicle/include/icicle/curves/montgomery_conversion.h:22-51; cpu_mont_conversion.cpp:11-27) */
+B200_API int b200_affine_convert_montgomery(int curve, const void* in, uint64_t n, int is_into, const b200_vec_ops_config* cfg, void* out);
+B200_API int b200_projective_convert_montgomery(int curve, const void* in, uint64_t n, int is_into, const b200_vec_ops_config* cfg, void* out);
+
+/* library version / build info string (static storage) */
+B200_API const char* b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICICLE_B200_H */
