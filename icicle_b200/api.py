@@ -1,0 +1,434 @@
+"""Host-side mirror of the reference's MSM / NTT / vec-ops frontend (icicle/include/icicle/{msm,ntt,vec_ops}.h) over the
+C ABI.  Same names, argument meaning and error behaviour as the reference API so that tests read like the reference's own
+(icicle/tests/test_curve_api.cpp, test_mod_arithmetic_api.h).  Host data = numpy uint32 limb arrays; device data =
+torch CUDA tensors (dtype int32/uint8/...; only the pointer is used) -- torch is plumbing for device memory, not compute.
+
+Nothing here computes: every function forwards to libicicle_b200.so and raises IcicleError on failure.
+"""
+import ctypes as C
+import enum
+
+import numpy as np
+
+from . import capi
+from .capi import IcicleError, MsmConfigC, NttConfigC, VecOpsConfigC, lib, check
+
+
+class Field(enum.IntEnum):
+    BN254_FR = 0
+    BN254_FQ = 1
+    BLS12_381_FR = 2
+    BLS12_381_FQ = 3
+    BLS12_377_FR = 4
+    BLS12_377_FQ = 5
+    BW6_761_FQ = 6
+    STARK252 = 7
+    BABYBEAR = 8
+    KOALABEAR = 9
+
+
+FIELD_NAMES = {Field.BN254_FR: "bn254_fr", Field.BN254_FQ: "bn254_fq", Field.BLS12_381_FR: "bls12_381_fr",
+               Field.BLS12_381_FQ: "bls12_381_fq", Field.BLS12_377_FR: "bls12_377_fr", Field.BLS12_377_FQ: "bls12_377_fq",
+               Field.BW6_761_FQ: "bw6_761_fq", Field.STARK252: "stark252", Field.BABYBEAR: "babybear", Field.KOALABEAR: "koalabear"}
+
+
+class Curve(enum.IntEnum):
+    BN254_G1 = 0
+    BN254_G2 = 1
+    BLS12_381_G1 = 2
+    BLS12_381_G2 = 3
+    BLS12_377_G1 = 4
+    BLS12_377_G2 = 5
+    BW6_761_G1 = 6
+    BW6_761_G2 = 7
+    GRUMPKIN = 8
+
+
+class NTTDir(enum.IntEnum):  # icicle/include/icicle/ntt.h:23-26
+    kForward = 0
+    kInverse = 1
+
+
+class Ordering(enum.IntEnum):  # icicle/include/icicle/ntt.h:37-44
+    kNN = 0
+    kNR = 1
+    kRN = 2
+    kRR = 3
+    kNM = 4
+    kMN = 5
+
+
+class VecOp(enum.IntEnum):
+    ADD = 0
+    SUB = 1
+    MUL = 2
+    ACCUMULATE = 3
+    SCALAR_ADD_VEC = 4
+    SCALAR_SUB_VEC = 5
+    SCALAR_MUL_VEC = 6
+
+
+def field_limbs(field):
+    return lib.b200_field_bytes(int(field)) // 4
+
+
+def scalar_field(curve):
+    return Field(lib.b200_curve_scalar_field(int(curve)))
+
+
+def affine_limbs(curve):
+    return lib.b200_curve_affine_bytes(int(curve)) // 4
+
+
+def projective_limbs(curve):
+    return lib.b200_curve_projective_bytes(int(curve)) // 4
+
+
+# ---- buffers ----------------------------------------------------------------------------------------------------------
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def is_on_device(x):
+    return _is_torch(x) and x.is_cuda
+
+
+def _ptr(x):
+    """(pointer, on_device, keepalive)"""
+    if _is_torch(x):
+        if not x.is_contiguous():
+            raise ValueError("device/host tensors must be contiguous")
+        return x.data_ptr(), bool(x.is_cuda), x
+    a = np.ascontiguousarray(x)
+    return a.ctypes.data, False, a
+
+
+def _stream_handle(stream):
+    if stream is None:
+        return None
+    if hasattr(stream, "cuda_stream"):
+        return stream.cuda_stream
+    return int(stream)
+
+
+def device_empty(n_limbs_total, device=None):
+    import torch
+    return torch.empty(int(n_limbs_total), dtype=torch.int32, device=device or "cuda")
+
+
+def to_device(host_array, device=None, stream=None):
+    import torch
+    a = np.ascontiguousarray(host_array, dtype=np.uint32)
+    t = torch.empty(a.size, dtype=torch.int32, device=device or "cuda")
+    check(lib.b200_copy_to_device(t.data_ptr(), a.ctypes.data, a.nbytes, _stream_handle(stream), 0), "copy_to_device")
+    return t.view(*a.shape)
+
+
+def to_host(dev_tensor, shape=None):
+    n = dev_tensor.numel() * dev_tensor.element_size() // 4
+    out = np.empty(n, dtype=np.uint32)
+    check(lib.b200_copy_to_host(out.ctypes.data, dev_tensor.data_ptr(), out.nbytes, None, 0), "copy_to_host")
+    return out.reshape(shape if shape is not None else tuple(dev_tensor.shape))
+
+
+def set_device(device_id):
+    check(lib.b200_set_device(int(device_id)), "set_device")
+
+
+def get_device_count():
+    n = C.c_int(0)
+    check(lib.b200_get_device_count(C.byref(n)), "get_device_count")
+    return n.value
+
+
+# ---- MSM --------------------------------------------------------------------------------------------------------------
+class MSMConfig:
+    """icicle::MSMConfig (icicle/include/icicle/msm.h:21-53); defaults of default_msm_config() (msm.h:60-78)."""
+
+    def __init__(self, **kw):
+        self.stream = None
+        self.precompute_factor = 1
+        self.c = 0
+        self.bitsize = 0
+        self.batch_size = 1
+        self.are_points_shared_in_batch = True
+        self.are_scalars_on_device = False
+        self.are_scalars_montgomery_form = False
+        self.are_points_on_device = False
+        self.are_points_montgomery_form = False
+        self.are_results_on_device = False
+        self.is_async = False
+        self.ext = {}  # backend extension keys: large_bucket_factor, nof_chunks, is_big_triangle (backend/msm_config.h:10-17)
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise TypeError(f"MSMConfig has no field {k}")
+            setattr(self, k, v)
+
+    def _c(self):
+        c = MsmConfigC()
+        lib.b200_msm_default_config(C.byref(c))
+        c.stream = _stream_handle(self.stream)
+        for k in ("precompute_factor", "c", "bitsize", "batch_size"):
+            setattr(c, k, int(getattr(self, k)))
+        for k in ("are_points_shared_in_batch", "are_scalars_on_device", "are_scalars_montgomery_form", "are_points_on_device",
+                  "are_points_montgomery_form", "are_results_on_device", "is_async"):
+            setattr(c, k, 1 if getattr(self, k) else 0)
+        c.ext_large_bucket_factor = int(self.ext.get("large_bucket_factor", 0))
+        c.ext_nof_chunks = int(self.ext.get("nof_chunks", 0))
+        c.ext_is_big_triangle = int(bool(self.ext.get("is_big_triangle", False)))
+        return c
+
+
+def default_msm_config():
+    return MSMConfig()
+
+
+def msm(curve, scalars, bases, msm_size, config=None, results=None):
+    """icicle::msm (icicle/include/icicle/msm.h:93-94 -> src/msm.cpp:12-16).  Returns `results`:
+    (batch, 3*coord_limbs) uint32 homogeneous projective points in standard form."""
+    cfg = config or MSMConfig()
+    sp, s_dev, _ks = _ptr(scalars)
+    bp, b_dev, _kb = _ptr(bases)
+    cfg.are_scalars_on_device = s_dev
+    cfg.are_points_on_device = b_dev
+    if results is None:
+        if cfg.are_results_on_device:
+            results = device_empty(cfg.batch_size * projective_limbs(curve)).view(cfg.batch_size, -1)
+        else:
+            results = np.zeros((cfg.batch_size, projective_limbs(curve)), dtype=np.uint32)
+    rp, r_dev, _kr = _ptr(results)
+    cfg.are_results_on_device = r_dev
+    c = cfg._c()
+    check(lib.b200_msm(int(curve), sp, bp, int(msm_size), C.byref(c), rp), "msm")
+    return results
+
+
+def msm_precompute_bases(curve, bases, nof_bases, config, output=None):
+    """icicle::msm_precompute_bases (msm.h:106-107)."""
+    cfg = config
+    bp, b_dev, _kb = _ptr(bases)
+    cfg.are_points_on_device = b_dev
+    if output is None:
+        n = nof_bases * cfg.precompute_factor
+        output = (device_empty(n * affine_limbs(curve)).view(n, -1) if cfg.are_results_on_device
+                  else np.zeros((n, affine_limbs(curve)), dtype=np.uint32))
+    op, o_dev, _ko = _ptr(output)
+    cfg.are_results_on_device = o_dev
+    c = cfg._c()
+    check(lib.b200_msm_precompute_bases(int(curve), bp, int(nof_bases), C.byref(c), op), "msm_precompute_bases")
+    return output
+
+
+def msm_choose_c(curve, msm_size, config=None):
+    c = (config or MSMConfig())._c()
+    return lib.b200_msm_choose_c(int(curve), int(msm_size), C.byref(c))
+
+
+# ---- NTT --------------------------------------------------------------------------------------------------------------
+class NTTConfig:
+    """icicle::NTTConfig<S> (icicle/include/icicle/ntt.h:52-64); defaults of default_ntt_config() (ntt.h:73-86)."""
+
+    def __init__(self, **kw):
+        self.stream = None
+        self.coset_gen = None  # (limbs,) uint32 standard form, None = one
+        self.batch_size = 1
+        self.columns_batch = False
+        self.ordering = Ordering.kNN
+        self.are_inputs_on_device = False
+        self.are_outputs_on_device = False
+        self.is_async = False
+        self.ext = {}  # ntt_algorithm (0 auto / 1 radix2 / 2 mixed radix), fast_twiddles (backend/ntt_config.h:7-18)
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise TypeError(f"NTTConfig has no field {k}")
+            setattr(self, k, v)
+
+    def _c(self):
+        c = NttConfigC()
+        lib.b200_ntt_default_config(C.byref(c))
+        c.stream = _stream_handle(self.stream)
+        self._coset_keep = None
+        if self.coset_gen is not None:
+            self._coset_keep = np.ascontiguousarray(self.coset_gen, dtype=np.uint32)
+            c.coset_gen = self._coset_keep.ctypes.data
+        c.batch_size = int(self.batch_size)
+        c.columns_batch = 1 if self.columns_batch else 0
+        c.are_inputs_on_device = 1 if self.are_inputs_on_device else 0
+        c.are_outputs_on_device = 1 if self.are_outputs_on_device else 0
+        c.is_async = 1 if self.is_async else 0
+        c.ordering = int(self.ordering)
+        c.ext_ntt_algorithm = int(self.ext.get("ntt_algorithm", 0))
+        c.ext_fast_twiddles = int(bool(self.ext.get("fast_twiddles", False)))
+        return c
+
+
+def default_ntt_config():
+    return NTTConfig()
+
+
+def ntt_init_domain(field, primitive_root, stream=None):
+    """icicle::ntt_init_domain (icicle/include/icicle/ntt.h:117 -> src/ntt.cpp:26-30)."""
+    r = np.ascontiguousarray(primitive_root, dtype=np.uint32)
+    check(lib.b200_ntt_init_domain(int(field), r.ctypes.data, _stream_handle(stream)), "ntt_init_domain")
+
+
+def ntt_release_domain(field):
+    check(lib.b200_ntt_release_domain(int(field)), "ntt_release_domain")
+
+
+def get_root_of_unity_from_domain(field, logn):
+    out = np.zeros(field_limbs(field), dtype=np.uint32)
+    check(lib.b200_ntt_get_root_of_unity_from_domain(int(field), int(logn), out.ctypes.data), "get_root_of_unity_from_domain")
+    return out
+
+
+def ntt(field, input, size, direction, config=None, output=None):
+    """icicle::ntt (icicle/include/icicle/ntt.h:108 -> src/ntt.cpp:11-15)."""
+    cfg = config or NTTConfig()
+    ip, i_dev, _ki = _ptr(input)
+    cfg.are_inputs_on_device = i_dev
+    if output is None:
+        n = size * cfg.batch_size * field_limbs(field)
+        output = device_empty(n) if cfg.are_outputs_on_device else np.zeros((size * cfg.batch_size, field_limbs(field)), dtype=np.uint32)
+    op, o_dev, _ko = _ptr(output)
+    cfg.are_outputs_on_device = o_dev
+    c = cfg._c()
+    check(lib.b200_ntt(int(field), ip, int(size), int(direction), C.byref(c), op), "ntt")
+    return output
+
+
+# ---- vec ops ----------------------------------------------------------------------------------------------------------
+class VecOpsConfig:
+    """icicle::VecOpsConfig (icicle/include/icicle/vec_ops.h:19-44)."""
+
+    def __init__(self, **kw):
+        self.stream = None
+        self.is_a_on_device = False
+        self.is_b_on_device = False
+        self.is_result_on_device = False
+        self.is_async = False
+        self.batch_size = 1
+        self.columns_batch = False
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise TypeError(f"VecOpsConfig has no field {k}")
+            setattr(self, k, v)
+
+    def _c(self):
+        c = VecOpsConfigC()
+        lib.b200_vec_ops_default_config(C.byref(c))
+        c.stream = _stream_handle(self.stream)
+        c.is_a_on_device = 1 if self.is_a_on_device else 0
+        c.is_b_on_device = 1 if self.is_b_on_device else 0
+        c.is_result_on_device = 1 if self.is_result_on_device else 0
+        c.is_async = 1 if self.is_async else 0
+        c.batch_size = int(self.batch_size)
+        c.columns_batch = 1 if self.columns_batch else 0
+        return c
+
+
+def _out_like(field, n_elems, on_device):
+    if on_device:
+        return device_empty(n_elems * field_limbs(field)).view(n_elems, -1)
+    return np.zeros((n_elems, field_limbs(field)), dtype=np.uint32)
+
+
+def _vec2(field, op, a, b, size, config, output):
+    cfg = config or VecOpsConfig()
+    ap, a_dev, _ka = _ptr(a)
+    bp, b_dev, _kb = _ptr(b)
+    cfg.is_a_on_device, cfg.is_b_on_device = a_dev, b_dev
+    if op == VecOp.ACCUMULATE:
+        output, op_ptr = a, ap
+    else:
+        if output is None:
+            output = _out_like(field, size * cfg.batch_size, cfg.is_result_on_device)
+        op_ptr, o_dev, _ko = _ptr(output)
+        cfg.is_result_on_device = o_dev
+    c = cfg._c()
+    check(lib.b200_vec_op(int(field), int(op), ap, bp, int(size), C.byref(c), op_ptr), f"vec_op({VecOp(op).name})")
+    return output
+
+
+def vector_add(field, a, b, size, config=None, output=None):
+    return _vec2(field, VecOp.ADD, a, b, size, config, output)
+
+
+def vector_sub(field, a, b, size, config=None, output=None):
+    return _vec2(field, VecOp.SUB, a, b, size, config, output)
+
+
+def vector_mul(field, a, b, size, config=None, output=None):
+    return _vec2(field, VecOp.MUL, a, b, size, config, output)
+
+
+def vector_accumulate(field, a, b, size, config=None):
+    return _vec2(field, VecOp.ACCUMULATE, a, b, size, config, None)
+
+
+def scalar_add_vec(field, scalar_a, b, size, config=None, output=None):
+    return _vec2(field, VecOp.SCALAR_ADD_VEC, scalar_a, b, size, config, output)
+
+
+def scalar_sub_vec(field, scalar_a, b, size, config=None, output=None):
+    return _vec2(field, VecOp.SCALAR_SUB_VEC, scalar_a, b, size, config, output)
+
+
+def scalar_mul_vec(field, scalar_a, b, size, config=None, output=None):
+    return _vec2(field, VecOp.SCALAR_MUL_VEC, scalar_a, b, size, config, output)
+
+
+def _unary(fn_name, field_or_curve, a, n_out_elems, limbs, config, output, *extra):
+    cfg = config or VecOpsConfig()
+    ap, a_dev, _ka = _ptr(a)
+    cfg.is_a_on_device = a_dev
+    if output is None:
+        output = (device_empty(n_out_elems * limbs).view(n_out_elems, -1) if cfg.is_result_on_device
+                  else np.zeros((n_out_elems, limbs), dtype=np.uint32))
+    op, o_dev, _ko = _ptr(output)
+    cfg.is_result_on_device = o_dev
+    c = cfg._c()
+    fn = getattr(lib, fn_name)
+    return fn, ap, op, c, output
+
+
+def convert_montgomery(field, a, size, is_into, config=None, output=None):
+    cfg = config or VecOpsConfig()
+    fn, ap, op, c, output = _unary("b200_convert_montgomery", field, a, size * cfg.batch_size, field_limbs(field), cfg, output)
+    check(fn(int(field), ap, int(size), 1 if is_into else 0, C.byref(c), op), "convert_montgomery")
+    return output
+
+
+def bit_reverse(field, a, size, config=None, output=None):
+    cfg = config or VecOpsConfig()
+    fn, ap, op, c, output = _unary("b200_bit_reverse", field, a, size * cfg.batch_size, field_limbs(field), cfg, output)
+    check(fn(int(field), ap, int(size), C.byref(c), op), "bit_reverse")
+    return output
+
+
+def matrix_transpose(field, a, rows, cols, config=None, output=None):
+    cfg = config or VecOpsConfig()
+    fn, ap, op, c, output = _unary("b200_matrix_transpose", field, a, rows * cols * cfg.batch_size, field_limbs(field), cfg, output)
+    check(fn(int(field), ap, int(rows), int(cols), C.byref(c), op), "matrix_transpose")
+    return output
+
+
+def slice(field, a, offset, stride, size_in, size_out, config=None, output=None):
+    cfg = config or VecOpsConfig()
+    fn, ap, op, c, output = _unary("b200_slice", field, a, size_out * cfg.batch_size, field_limbs(field), cfg, output)
+    check(fn(int(field), ap, int(offset), int(stride), int(size_in), int(size_out), C.byref(c), op), "slice")
+    return output
+
+
+def affine_convert_montgomery(curve, a, n, is_into, config=None, output=None):
+    cfg = config or VecOpsConfig()
+    fn, ap, op, c, output = _unary("b200_affine_convert_montgomery", curve, a, n, affine_limbs(curve), cfg, output)
+    check(fn(int(curve), ap, int(n), 1 if is_into else 0, C.byref(c), op), "affine_convert_montgomery")
+    return output
+
+
+def projective_convert_montgomery(curve, a, n, is_into, config=None, output=None):
+    cfg = config or VecOpsConfig()
+    fn, ap, op, c, output = _unary("b200_projective_convert_montgomery", curve, a, n, projective_limbs(curve), cfg, output)
+    check(fn(int(curve), ap, int(n), 1 if is_into else 0, C.byref(c), op), "projective_convert_montgomery")
+    return output

@@ -1,0 +1,120 @@
+// libicicle_backend_cuda_field_<field>.so : NTT + vec-ops registrations for one scalar field.
+// Hooks used (icicle/include/icicle/backend/ntt_backend.h:23,57,72,85; vec_ops_backend.h:87-226):
+//   REGISTER_NTT_BACKEND, REGISTER_NTT_INIT_DOMAIN_BACKEND, REGISTER_NTT_RELEASE_DOMAIN_BACKEND,
+//   REGISTER_NTT_GET_ROU_FROM_DOMAIN_BACKEND, REGISTER_VECTOR_{ADD,ACCUMULATE,SUB,MUL}_BACKEND,
+//   REGISTER_SCALAR_{MUL,ADD,SUB}_VEC_BACKEND, REGISTER_CONVERT_MONTGOMERY_BACKEND, REGISTER_BIT_REVERSE_BACKEND,
+//   REGISTER_SLICE_BACKEND, REGISTER_MATRIX_TRANSPOSE_BACKEND.
+// Each lambda translates the reference config (ntt.h:52-64, vec_ops.h:19-44) to the C structs and forwards.
+#include "shim_common.h"
+#include "icicle/vec_ops.h"
+#include "icicle/backend/vec_ops_backend.h"
+#include "icicle/fields/field_config.h"
+#ifdef NTT
+  #include "icicle/ntt.h"
+  #include "icicle/backend/ntt_backend.h"
+  #include "icicle/backend/ntt_config.h"
+#endif
+
+using namespace icicle;
+using namespace field_config;
+using namespace b200_shim;
+
+namespace {
+
+  constexpr int FIELD = scalar_field_id();
+  static_assert(FIELD >= 0, "this field has no B200 backend");
+
+  b200_vec_ops_config to_c(const VecOpsConfig& c)
+  {
+    b200_vec_ops_config o;
+    b200_vec_ops_default_config(&o);
+    o.stream = c.stream;
+    o.is_a_on_device = c.is_a_on_device;
+    o.is_b_on_device = c.is_b_on_device;
+    o.is_result_on_device = c.is_result_on_device;
+    o.is_async = c.is_async;
+    o.batch_size = c.batch_size;
+    o.columns_batch = c.columns_batch;
+    return o;
+  }
+
+  template <int OP>
+  eIcicleError vec2(const Device&, const scalar_t* a, const scalar_t* b, uint64_t size, const VecOpsConfig& config, scalar_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_vec_op(FIELD, OP, a, b, size, &c, out));
+  }
+  eIcicleError accumulate(const Device&, scalar_t* a, const scalar_t* b, uint64_t size, const VecOpsConfig& config)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_vec_op(FIELD, B200_VEC_ACCUMULATE, a, b, size, &c, a));
+  }
+  eIcicleError convert_mont(const Device&, const scalar_t* in, uint64_t size, bool is_into, const VecOpsConfig& config, scalar_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_convert_montgomery(FIELD, in, size, is_into, &c, out));
+  }
+  eIcicleError bit_rev(const Device&, const scalar_t* in, uint64_t size, const VecOpsConfig& config, scalar_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_bit_reverse(FIELD, in, size, &c, out));
+  }
+  eIcicleError slice_op(const Device&, const scalar_t* in, uint64_t offset, uint64_t stride, uint64_t size_in, uint64_t size_out,
+                        const VecOpsConfig& config, scalar_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_slice(FIELD, in, offset, stride, size_in, size_out, &c, out));
+  }
+  eIcicleError transpose(const Device&, const scalar_t* in, uint32_t rows, uint32_t cols, const VecOpsConfig& config, scalar_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_matrix_transpose(FIELD, in, rows, cols, &c, out));
+  }
+
+#ifdef NTT
+  eIcicleError ntt_impl(const Device&, const scalar_t* in, int size, NTTDir dir, const NTTConfig<scalar_t>& config, scalar_t* out)
+  {
+    b200_ntt_config c;
+    b200_ntt_default_config(&c);
+    c.stream = config.stream;
+    c.coset_gen = &config.coset_gen;
+    c.batch_size = config.batch_size;
+    c.columns_batch = config.columns_batch;
+    c.are_inputs_on_device = config.are_inputs_on_device;
+    c.are_outputs_on_device = config.are_outputs_on_device;
+    c.is_async = config.is_async;
+    c.ordering = static_cast<int>(config.ordering);
+    c.ext_ntt_algorithm = ext_int(config.ext, CudaBackendConfig::CUDA_NTT_ALGORITHM, 0);
+    c.ext_fast_twiddles = ext_int(config.ext, CudaBackendConfig::CUDA_NTT_FAST_TWIDDLES_MODE, 0);
+    return to_err(b200_ntt(FIELD, in, size, dir == NTTDir::kForward ? B200_NTT_FORWARD : B200_NTT_INVERSE, &c, out));
+  }
+  eIcicleError ntt_init(const Device&, const scalar_t& root, const NTTInitDomainConfig& config)
+  {
+    return to_err(b200_ntt_init_domain(FIELD, &root, config.stream));
+  }
+  eIcicleError ntt_release(const Device&, const scalar_t&) { return to_err(b200_ntt_release_domain(FIELD)); }
+  eIcicleError ntt_rou(const Device&, uint64_t logn, scalar_t* rou)
+  {
+    return to_err(b200_ntt_get_root_of_unity_from_domain(FIELD, logn, rou));
+  }
+#endif
+
+} // namespace
+
+REGISTER_VECTOR_ADD_BACKEND(B200_DEVICE_TYPE, vec2<B200_VEC_ADD>);
+REGISTER_VECTOR_SUB_BACKEND(B200_DEVICE_TYPE, vec2<B200_VEC_SUB>);
+REGISTER_VECTOR_MUL_BACKEND(B200_DEVICE_TYPE, vec2<B200_VEC_MUL>);
+REGISTER_VECTOR_ACCUMULATE_BACKEND(B200_DEVICE_TYPE, accumulate);
+REGISTER_SCALAR_ADD_VEC_BACKEND(B200_DEVICE_TYPE, vec2<B200_SCALAR_ADD_VEC>);
+REGISTER_SCALAR_SUB_VEC_BACKEND(B200_DEVICE_TYPE, vec2<B200_SCALAR_SUB_VEC>);
+REGISTER_SCALAR_MUL_VEC_BACKEND(B200_DEVICE_TYPE, vec2<B200_SCALAR_MUL_VEC>);
+REGISTER_CONVERT_MONTGOMERY_BACKEND(B200_DEVICE_TYPE, convert_mont);
+REGISTER_BIT_REVERSE_BACKEND(B200_DEVICE_TYPE, bit_rev);
+REGISTER_SLICE_BACKEND(B200_DEVICE_TYPE, slice_op);
+REGISTER_MATRIX_TRANSPOSE_BACKEND(B200_DEVICE_TYPE, transpose);
+#ifdef NTT
+REGISTER_NTT_BACKEND(B200_DEVICE_TYPE, ntt_impl);
+REGISTER_NTT_INIT_DOMAIN_BACKEND(B200_DEVICE_TYPE, ntt_init);
+REGISTER_NTT_RELEASE_DOMAIN_BACKEND(B200_DEVICE_TYPE, ntt_release);
+REGISTER_NTT_GET_ROU_FROM_DOMAIN_BACKEND(B200_DEVICE_TYPE, ntt_rou);
+#endif
