@@ -219,6 +219,14 @@ def msm_precompute_bases(curve, bases, nof_bases, config, output=None):
     return output
 
 
+def ec_sum(curve, points, n, config=None, output=None):
+    """Sum of n projective points (multi-GPU partial-result combine; see b200_ec_sum in include/icicle_b200.h)."""
+    cfg = config or VecOpsConfig()
+    fn, ap, op, c, output = _unary("b200_ec_sum", curve, points, 1, projective_limbs(curve), cfg, output)
+    check(fn(int(curve), ap, int(n), C.byref(c), op), "ec_sum")
+    return output
+
+
 def msm_choose_c(curve, msm_size, config=None):
     c = (config or MSMConfig())._c()
     return lib.b200_msm_choose_c(int(curve), int(msm_size), C.byref(c))
@@ -432,3 +440,22 @@ def projective_convert_montgomery(curve, a, n, is_into, config=None, output=None
     fn, ap, op, c, output = _unary("b200_projective_convert_montgomery", curve, a, n, projective_limbs(curve), cfg, output)
     check(fn(int(curve), ap, int(n), 1 if is_into else 0, C.byref(c), op), "projective_convert_montgomery")
     return output
+
+
+# ---- instrumentation ----------------------------------------------------------------------------------------------------
+def launch_count():
+    """Kernels of libicicle_b200.so launched so far in this process."""
+    return int(lib.b200_get_launch_count())
+
+
+def set_profiling(on):
+    lib.b200_set_profiling(1 if on else 0)
+
+
+def last_profile():
+    """(what, [(stage, ms), ...]) of the last call made while profiling was on."""
+    names = C.create_string_buffer(512)
+    ms = (C.c_float * 16)()
+    k = lib.b200_get_last_profile(names, 512, ms, 16)
+    parts = names.value.decode().split(",")
+    return parts[0], [(parts[1 + i], float(ms[i])) for i in range(k)]

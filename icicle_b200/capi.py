@@ -76,6 +76,7 @@ SYMBOLS = {
     "b200_msm_default_config": (None, [C.POINTER(MsmConfigC)]),
     "b200_msm": (_i, [_i, _vp, _vp, _i, C.POINTER(MsmConfigC), _vp]),
     "b200_msm_precompute_bases": (_i, [_i, _vp, _i, C.POINTER(MsmConfigC), _vp]),
+    "b200_ec_sum": (_i, [_i, _vp, _i, C.POINTER(VecOpsConfigC), _vp]),
     "b200_msm_choose_c": (_i, [_i, _i, C.POINTER(MsmConfigC)]),
     "b200_ntt_default_config": (None, [C.POINTER(NttConfigC)]),
     "b200_ntt_init_domain": (_i, [_i, _vp, _vp]),
@@ -90,6 +91,9 @@ SYMBOLS = {
     "b200_slice": (_i, [_i, _vp, _u64, _u64, _u64, _u64, C.POINTER(VecOpsConfigC), _vp]),
     "b200_affine_convert_montgomery": (_i, [_i, _vp, _u64, _i, C.POINTER(VecOpsConfigC), _vp]),
     "b200_projective_convert_montgomery": (_i, [_i, _vp, _u64, _i, C.POINTER(VecOpsConfigC), _vp]),
+    "b200_get_launch_count": (C.c_longlong, []),
+    "b200_set_profiling": (None, [_i]),
+    "b200_get_last_profile": (_i, [C.c_char_p, _i, C.POINTER(C.c_float), _i]),
     "b200_version": (C.c_char_p, []),
 }
 

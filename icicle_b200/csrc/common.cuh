@@ -91,6 +91,24 @@ static inline int finish_out(void* dst, const void* dev_ptr, size_t bytes, bool 
   return B200_SUCCESS;
 }
 
+// ---- instrumentation: launch counter (bench.py reports it as gpu_launches) and optional per-stage CUDA-event timing -----
+extern "C" B200_API void b200_count_launch(int n);
+#define B200_LAUNCHED(n) b200_count_launch(n)
+
+struct StageTimer {
+  // Records an event per stage boundary on the launching stream when profiling is on (b200_set_profiling);
+  // b200_get_last_profile() reports the elapsed times of the last completed call.
+  static constexpr int MAX_STAGES = 12;
+  cudaEvent_t ev[MAX_STAGES + 1];
+  const char* names[MAX_STAGES];
+  int n = 0;
+  bool on = false;
+  cudaStream_t s = nullptr;
+  void begin(cudaStream_t stream);
+  void mark(const char* name);
+  void finish(const char* what);
+};
+
 static inline int num_sms()
 {
   static thread_local int cached_dev = -1, cached = 148;

@@ -6,7 +6,8 @@
 #define DECL(ID)                                                                                                       \
   extern "C" int b200_msm_entry_##ID(const void*, const void*, int, const b200_msm_config*, void*) __attribute__((weak)); \
   extern "C" int b200_msm_precompute_entry_##ID(const void*, int, const b200_msm_config*, void*) __attribute__((weak)); \
-  extern "C" int b200_msm_plan_c_entry_##ID(int, const b200_msm_config*) __attribute__((weak));
+  extern "C" int b200_msm_plan_c_entry_##ID(int, const b200_msm_config*) __attribute__((weak));                         \
+  extern "C" int b200_ec_sum_entry_##ID(const void*, int, const b200_vec_ops_config*, void*) __attribute__((weak));
 DECL(0) DECL(1) DECL(2) DECL(3) DECL(4) DECL(5) DECL(6) DECL(8)
 
 #define CASE(ID, TU)                                                                                                   \
@@ -52,6 +53,15 @@ b200_msm_precompute_bases(int curve, const void* input_bases, int nof_bases, con
 {
   if (!cfg || !input_bases || !output_bases) return B200_INVALID_POINTER;
 #define CALL(TU) return b200_msm_precompute_entry_##TU(input_bases, nof_bases, cfg, output_bases)
+  ALL_CASES(CALL)
+#undef CALL
+}
+
+__attribute__((visibility("default"))) int
+b200_ec_sum(int curve, const void* points, int n, const b200_vec_ops_config* cfg, void* out)
+{
+  if (!cfg || !points || !out) return B200_INVALID_POINTER;
+#define CALL(TU) return b200_ec_sum_entry_##TU(points, n, cfg, out)
   ALL_CASES(CALL)
 #undef CALL
 }

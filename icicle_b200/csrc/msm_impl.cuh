@@ -181,6 +181,62 @@ __global__ void __launch_bounds__(MSM_THREADS) k_accumulate(
   }
 }
 
+// One level of the hierarchical stitch: each thread owns `seg` consecutive partial slots, sums the slots of each run
+// (runs are delimited by the start/end flags the previous level wrote), stores runs that both start and end inside its
+// segment straight to their bucket and emits at most two next-level partials (a run ending here that started earlier,
+// and a run still open at the end of the segment).  The slot list shrinks by seg/2 per level, so a bucket that spans
+// thousands of slices (top window, skewed scalars, bitsize = 1) is reduced in O(log) depth instead of by one thread.
+template <class F>
+__global__ void __launch_bounds__(MSM_THREADS) k_reduce_partials(
+  const uint32_t* __restrict__ in_key, const uint32_t* __restrict__ in_flag, const uint32_t* __restrict__ in_pt, uint64_t n_in,
+  uint32_t seg, uint32_t* __restrict__ out_key, uint32_t* __restrict__ out_flag, uint32_t* __restrict__ out_pt, uint64_t n_threads,
+  uint32_t* __restrict__ buckets)
+{
+  constexpr int XW = 4 * F::N;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_threads) return;
+  out_key[2 * t] = P_EMPTY;
+  out_key[2 * t + 1] = P_EMPTY;
+  const uint64_t beg = t * seg;
+  const uint64_t end = (beg + seg < n_in) ? beg + seg : n_in;
+  bool active = false, started = false;
+  uint32_t cur = 0;
+  int slot = 0;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint64_t j = beg; j < end; j++) {
+    const uint32_t key = in_key[j];
+    if (key == P_EMPTY) continue;
+    const uint32_t fl = in_flag[j];
+    XYZZ<F> o = load_xyzz<F>(in_pt + j * XW);
+    if (!active) {
+      acc = o;
+      cur = key;
+      started = (fl & 1u) != 0;
+      active = true;
+    } else {
+      acc.add(o);
+    }
+    if (fl & 2u) { // run ends at this slot
+      if (started) {
+        store_xyzz<F>(buckets + (uint64_t)cur * XW, acc);
+      } else {
+        const uint64_t ps = 2 * t + slot;
+        out_key[ps] = cur;
+        out_flag[ps] = 2u;
+        store_xyzz<F>(out_pt + ps * XW, acc);
+      }
+      slot = 1;
+      active = false;
+    }
+  }
+  if (active) { // run continues into the next segment
+    const uint64_t ps = 2 * t + slot;
+    out_key[ps] = cur;
+    out_flag[ps] = started ? 1u : 0u;
+    store_xyzz<F>(out_pt + ps * XW, acc);
+  }
+}
+
 // Stitch runs that span several slices: the slot that starts a run walks forward until the slot that ends it.
 template <class F>
 __global__ void __launch_bounds__(MSM_THREADS) k_resolve(
@@ -439,7 +495,7 @@ int msm_impl(const void* scalars, const void* bases, int msm_size, const b200_ms
     }
     const uint64_t ncoord = n_points * 2 * (F::N / B::N);
     unsigned g = (unsigned)std::min<uint64_t>((ncoord + 255) / 256, (uint64_t)num_sms() * 16);
-    k_to_mont<B><<<g, 256, 0, s>>>((const uint32_t*)d_pts, dst, ncoord);
+    k_to_mont<B><<<g, 256, 0, s>>>((const uint32_t*)d_pts, dst, ncoord); B200_LAUNCHED(1);
     B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     pts_m = dst;
   }
@@ -470,7 +526,7 @@ int msm_impl(const void* scalars, const void* bases, int msm_size, const b200_ms
   if (chunk_log > pl.c - 1) chunk_log = pl.c - 1;
   const uint64_t max_chunks = max_buckets >> chunk_log;
 
-  Scratch s_k0, s_k1, s_v0, s_v1, s_cub, s_bkt, s_pkey, s_pflag, s_ppt, s_red0, s_red1;
+  Scratch s_k0, s_k1, s_v0, s_v1, s_cub, s_bkt, s_pkey, s_pflag, s_ppt, s_pkey2, s_pflag2, s_ppt2, s_red0, s_red1;
   if ((err = s_k0.alloc(max_ent * 4, s))) return err;
   if ((err = s_k1.alloc(max_ent * 4, s))) return err;
   if ((err = s_v0.alloc(max_ent * 4, s))) return err;
@@ -485,9 +541,15 @@ int msm_impl(const void* scalars, const void* bases, int msm_size, const b200_ms
   if ((err = s_pkey.alloc(max_slices * 2 * 4, s))) return err;
   if ((err = s_pflag.alloc(max_slices * 2 * 4, s))) return err;
   if ((err = s_ppt.alloc(max_slices * 2 * XW * 4, s))) return err;
+  const uint64_t max_slots2 = 2 * ((max_slices * 2 + 15) / 16) + 2;
+  if ((err = s_pkey2.alloc(max_slots2 * 4, s))) return err;
+  if ((err = s_pflag2.alloc(max_slots2 * 4, s))) return err;
+  if ((err = s_ppt2.alloc(max_slots2 * XW * 4, s))) return err;
   if ((err = s_red0.alloc(std::max<uint64_t>(max_chunks, 1) * XW * 4, s))) return err;
   if ((err = s_red1.alloc(std::max<uint64_t>(max_chunks / 2 + 1, 1) * XW * 4, s))) return err;
 
+  StageTimer prof;
+  prof.begin(s);
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int bl = std::min(chunk, batch - b0);
     const uint64_t n_ent = ent_per_msm * bl;
@@ -501,29 +563,49 @@ int msm_impl(const void* scalars, const void* bases, int msm_size, const b200_ms
     {
       uint64_t th = (uint64_t)n * bl;
       k_digits<S><<<(unsigned)((th + 255) / 256), 256, 0, s>>>(
-        sc, n, (uint32_t)bl, pl, cfg->are_scalars_montgomery_form, shared, s_k0.as<uint32_t>(), s_v0.as<uint32_t>(), sentinel);
+        sc, n, (uint32_t)bl, pl, cfg->are_scalars_montgomery_form, shared, s_k0.as<uint32_t>(), s_v0.as<uint32_t>(), sentinel); B200_LAUNCHED(1);
       B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     }
+    prof.mark("digits");
     // K7
     cub::DoubleBuffer<uint32_t> dk(s_k0.as<uint32_t>(), s_k1.as<uint32_t>()), dv(s_v0.as<uint32_t>(), s_v1.as<uint32_t>());
     {
       const int key_bits = std::max(1, ilog2_ceil((uint64_t)sentinel + 1));
       B200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s_cub.p, cub_bytes, dk, dv, (int64_t)n_ent, 0, key_bits, s), B200_UNKNOWN_ERROR);
     }
+    prof.mark("sort");
     // K8
     B200_CUDA_TRY(cudaMemsetAsync(s_bkt.p, 0, n_buckets * XW * 4, s), B200_UNKNOWN_ERROR);
     const uint64_t n_slices = (n_ent + slice - 1) / slice;
     k_accumulate<F><<<(unsigned)((n_slices + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
       dk.Current(), dv.Current(), n_ent, slice, sentinel, pts, s_bkt.as<uint32_t>(), s_pkey.as<uint32_t>(), s_pflag.as<uint32_t>(),
-      s_ppt.as<uint32_t>(), n_slices);
+      s_ppt.as<uint32_t>(), n_slices); B200_LAUNCHED(1);
     B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
-    k_resolve<F><<<(unsigned)((2 * n_slices + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
-      s_pkey.as<uint32_t>(), s_pflag.as<uint32_t>(), s_ppt.as<uint32_t>(), 2 * n_slices, s_bkt.as<uint32_t>());
-    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    prof.mark("accumulate");
+    {
+      // hierarchical stitch of the boundary partials (see k_reduce_partials), then a final owner walk over <= 512 slots
+      uint32_t *ik = s_pkey.as<uint32_t>(), *ifl = s_pflag.as<uint32_t>(), *ipt = s_ppt.as<uint32_t>();
+      uint32_t *ok = s_pkey2.as<uint32_t>(), *ofl = s_pflag2.as<uint32_t>(), *opt = s_ppt2.as<uint32_t>();
+      uint64_t n_slots = 2 * n_slices;
+      const uint32_t seg = 16;
+      while (n_slots > 512) {
+        const uint64_t nt = (n_slots + seg - 1) / seg;
+        k_reduce_partials<F><<<(unsigned)((nt + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
+          ik, ifl, ipt, n_slots, seg, ok, ofl, opt, nt, s_bkt.as<uint32_t>()); B200_LAUNCHED(1);
+        B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+        std::swap(ik, ok);
+        std::swap(ifl, ofl);
+        std::swap(ipt, opt);
+        n_slots = 2 * nt;
+      }
+      k_resolve<F><<<(unsigned)((n_slots + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(ik, ifl, ipt, n_slots, s_bkt.as<uint32_t>()); B200_LAUNCHED(1);
+      B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    }
+    prof.mark("resolve");
     // K9
     const uint64_t n_chunks = n_buckets >> chunk_log;
     k_bucket_chunks<F><<<(unsigned)((n_chunks + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
-      s_bkt.as<uint32_t>(), n_modules, (uint32_t)(pl.c - 1), (uint32_t)chunk_log, s_red0.as<uint32_t>());
+      s_bkt.as<uint32_t>(), n_modules, (uint32_t)(pl.c - 1), (uint32_t)chunk_log, s_red0.as<uint32_t>()); B200_LAUNCHED(1);
     B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     uint32_t* cur = s_red0.as<uint32_t>();
     uint32_t* other = s_red1.as<uint32_t>();
@@ -531,15 +613,18 @@ int msm_impl(const void* scalars, const void* bases, int msm_size, const b200_ms
     while (per_module > 1) {
       const uint32_t k = (uint32_t)std::min<uint64_t>(per_module, 8);
       const uint64_t n_out = (uint64_t)n_modules * (per_module / k);
-      k_sum_groups<F><<<(unsigned)((n_out + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(cur, other, n_out, k);
+      k_sum_groups<F><<<(unsigned)((n_out + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(cur, other, n_out, k); B200_LAUNCHED(1);
       B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
       std::swap(cur, other);
       per_module /= k;
     }
+    prof.mark("bucket_reduce");
     // K10
-    k_final<F><<<(bl + 31) / 32, 32, 0, s>>>(cur, (uint32_t)pl.nbm, (uint32_t)pl.c, (uint32_t)bl, (uint32_t*)d_res + (uint64_t)b0 * PW);
+    k_final<F><<<(bl + 31) / 32, 32, 0, s>>>(cur, (uint32_t)pl.nbm, (uint32_t)pl.c, (uint32_t)bl, (uint32_t*)d_res + (uint64_t)b0 * PW); B200_LAUNCHED(1);
     B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
   }
+  prof.mark("final");
+  prof.finish("msm");
   return finish_out(results, d_res, (size_t)batch * PW * 4, cfg->are_results_on_device, cfg->is_async, s);
 }
 
@@ -560,9 +645,48 @@ int precompute_impl(const void* in, int n, const b200_msm_config* cfg, void* out
   if ((err = stage_in(d_in, in, bytes_in, cfg->are_points_on_device, s, s_in))) return err;
   if ((err = stage_out(d_out, out, bytes_out, cfg->are_results_on_device, s, s_out))) return err;
   k_precompute<F><<<(n + MSM_THREADS - 1) / MSM_THREADS, MSM_THREADS, 0, s>>>(
-    (const uint32_t*)d_in, (uint32_t)n, (uint32_t)pl.pf, shift, cfg->are_points_montgomery_form, cfg->are_points_montgomery_form, (uint32_t*)d_out);
+    (const uint32_t*)d_in, (uint32_t)n, (uint32_t)pl.pf, shift, cfg->are_points_montgomery_form, cfg->are_points_montgomery_form, (uint32_t*)d_out); B200_LAUNCHED(1);
   B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
   return finish_out(out, d_out, bytes_out, cfg->are_results_on_device, cfg->is_async, s);
+}
+
+
+// K12: sum of n homogeneous projective points given in standard form (multi-GPU combine of per-GPU partial MSM results
+// after the NCCL all-gather; the reference has no multi-device reduction -- docs/docs/start/architecture/multi-device.md).
+template <class F>
+__global__ void k_proj_sum(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out)
+{
+  constexpr int PW = 3 * F::N;
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t i = 0; i < n; i++) {
+    Projective<F> p = {load_el<F>(in + (uint64_t)i * PW).to_mont(), load_el<F>(in + (uint64_t)i * PW + F::N).to_mont(),
+                       load_el<F>(in + (uint64_t)i * PW + 2 * F::N).to_mont()};
+    XYZZ<F> q = XYZZ<F>::from_projective(p);
+    acc.add(q);
+  }
+  Projective<F> r = acc.to_projective();
+  store_el(out, r.x.from_mont());
+  store_el(out + F::N, r.y.from_mont());
+  store_el(out + 2 * F::N, r.z.from_mont());
+}
+
+template <class C>
+int ec_sum_impl(const void* points, int n, const b200_vec_ops_config* cfg, void* out)
+{
+  typedef typename C::Base F;
+  constexpr int PW = 3 * F::N;
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  if (n <= 0) return B200_INVALID_ARGUMENT;
+  Scratch s_in, s_out;
+  const void* d_in;
+  void* d_out;
+  int err;
+  if ((err = stage_in(d_in, points, (size_t)n * PW * 4, cfg->is_a_on_device, s, s_in))) return err;
+  if ((err = stage_out(d_out, out, (size_t)PW * 4, cfg->is_result_on_device, s, s_out))) return err;
+  k_proj_sum<F><<<1, 32, 0, s>>>((const uint32_t*)d_in, (uint32_t)n, (uint32_t*)d_out); B200_LAUNCHED(1);
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  return finish_out(out, d_out, (size_t)PW * 4, cfg->is_result_on_device, cfg->is_async, s);
 }
 
 }} // namespace b200::msm

@@ -34,6 +34,11 @@ __attribute__((visibility("hidden"))) int B200_CAT(b200_msm_precompute_entry_, B
 {
   return precompute_impl<ThisCurve>(in, n, cfg, out);
 }
+__attribute__((visibility("hidden"))) int B200_CAT(b200_ec_sum_entry_, B200_MSM_CURVE)(
+  const void* points, int n, const b200_vec_ops_config* cfg, void* out)
+{
+  return ec_sum_impl<ThisCurve>(points, n, cfg, out);
+}
 __attribute__((visibility("hidden"))) int B200_CAT(b200_msm_plan_c_entry_, B200_MSM_CURVE)(int msm_size, const b200_msm_config* cfg)
 {
   return make_plan<ThisCurve>(msm_size, cfg).c;

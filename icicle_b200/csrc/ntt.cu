@@ -220,7 +220,7 @@ int launch_pass(const uint32_t* src, uint32_t* dst, const PassParams& p, cudaStr
 {
   uint64_t total = (1ull << (p.n_log - LOGR)) * p.batch;
   unsigned blocks = (unsigned)((total + 127) / 128);
-  k_ntt_pass<F, LOGR><<<blocks, 128, 0, s>>>(src, dst, p);
+  k_ntt_pass<F, LOGR><<<blocks, 128, 0, s>>>(src, dst, p); B200_LAUNCHED(1);
   B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
   return B200_SUCCESS;
 }
@@ -258,7 +258,7 @@ int init_domain_impl(Domain* d, const void* primitive_root, cudaStream_t s)
   uint32_t* aux = nullptr;
   B200_CUDA_TRY(cudaMalloc(&aux, (size_t)(MAX_LOG_DOMAIN + 1) * F::BYTES), B200_ALLOCATION_FAILED);
   B200_CUDA_TRY(cudaMemcpyAsync(root_d.p, primitive_root, F::BYTES, cudaMemcpyHostToDevice, s), B200_COPY_FAILED);
-  k_domain_setup<F><<<1, 1, 0, s>>>(root_d.as<uint32_t>(), info_d.as<uint32_t>(), aux, pw_d.as<uint32_t>());
+  k_domain_setup<F><<<1, 1, 0, s>>>(root_d.as<uint32_t>(), info_d.as<uint32_t>(), aux, pw_d.as<uint32_t>()); B200_LAUNCHED(1);
   uint32_t order = 0;
   B200_CUDA_TRY(cudaMemcpyAsync(&order, info_d.p, 4, cudaMemcpyDeviceToHost, s), B200_COPY_FAILED);
   B200_CUDA_TRY(cudaStreamSynchronize(s), B200_SYNCHRONIZATION_FAILED);
@@ -277,7 +277,7 @@ int init_domain_impl(Domain* d, const void* primitive_root, cudaStream_t s)
   }
   constexpr int CHUNK = 64;
   uint64_t threads = (size + CHUNK - 1) / CHUNK;
-  k_power_table<F, CHUNK><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(pw_d.as<uint32_t>(), nullptr, tw, size);
+  k_power_table<F, CHUNK><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(pw_d.as<uint32_t>(), nullptr, tw, size); B200_LAUNCHED(1);
   B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
   B200_CUDA_TRY(cudaStreamSynchronize(s), B200_SYNCHRONIZATION_FAILED);
   d->twiddles = tw;
@@ -343,12 +343,12 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
     if ((err = scoset_pw.alloc((size_t)40 * F::BYTES, s))) return err;
     if ((err = scoset_tab.alloc((size_t)size * F::BYTES, s))) return err;
     B200_CUDA_TRY(cudaMemcpyAsync(scoset_g.p, cfg->coset_gen, F::BYTES, cudaMemcpyHostToDevice, s), B200_COPY_FAILED);
-    k_coset_setup<F><<<1, 1, 0, s>>>(scoset_g.as<uint32_t>(), inverse ? 1 : 0, scoset_pw.as<uint32_t>());
+    k_coset_setup<F><<<1, 1, 0, s>>>(scoset_g.as<uint32_t>(), inverse ? 1 : 0, scoset_pw.as<uint32_t>()); B200_LAUNCHED(1);
     constexpr int CHUNK = 16;
     uint64_t threads = ((uint64_t)size + CHUNK - 1) / CHUNK;
     // forward: table[i] = g^i ; inverse: table[i] = N^-1 * g^-i
     k_power_table<F, CHUNK><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(
-      scoset_pw.as<uint32_t>(), inverse ? d->aux + (size_t)n_log * F::N : nullptr, scoset_tab.as<uint32_t>(), (uint64_t)size);
+      scoset_pw.as<uint32_t>(), inverse ? d->aux + (size_t)n_log * F::N : nullptr, scoset_tab.as<uint32_t>(), (uint64_t)size); B200_LAUNCHED(1);
     B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     if (inverse) out_mul = scoset_tab.as<uint32_t>();
     else in_mul = scoset_tab.as<uint32_t>();
@@ -388,6 +388,8 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
   p.bstride = cfg->columns_batch ? 1 : (uint64_t)size;
   p.estride = cfg->columns_batch ? batch : 1;
 
+  StageTimer prof;
+  prof.begin(s);
   const uint32_t* src = (const uint32_t*)din;
   int hi = n_log;
   for (int i = 0; i < npass; i++) {
@@ -412,9 +414,11 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
       dstp = work;
     }
     if ((err = launch_pass_r<F>(r, src, dstp, p, s))) return err;
+    prof.mark("pass");
     src = dstp;
     hi -= r;
   }
+  prof.finish("ntt");
   return finish_out(output, dout, bytes, cfg->are_outputs_on_device, cfg->is_async, s);
 }
 

@@ -6,7 +6,73 @@
 
 using namespace b200;
 
+#include <atomic>
+#include <mutex>
+#include <string>
+namespace {
+  std::atomic<long long> g_launches{0};
+  std::atomic<int> g_profiling{0};
+  std::mutex g_prof_mu;
+  std::string g_prof_what;
+  int g_prof_n = 0;
+  char g_prof_names[StageTimer::MAX_STAGES][32];
+  float g_prof_ms[StageTimer::MAX_STAGES];
+} // namespace
+
+namespace b200 {
+  void StageTimer::begin(cudaStream_t stream)
+  {
+    on = g_profiling.load() != 0;
+    s = stream;
+    n = 0;
+    if (!on) return;
+    cudaEventCreate(&ev[0]);
+    cudaEventRecord(ev[0], s);
+  }
+  void StageTimer::mark(const char* name)
+  {
+    if (!on || n >= MAX_STAGES) return;
+    names[n] = name;
+    cudaEventCreate(&ev[n + 1]);
+    cudaEventRecord(ev[n + 1], s);
+    n++;
+  }
+  void StageTimer::finish(const char* what)
+  {
+    if (!on) return;
+    cudaEventSynchronize(ev[n]);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_what = what;
+    g_prof_n = n;
+    for (int i = 0; i < n; i++) {
+      cudaEventElapsedTime(&g_prof_ms[i], ev[i], ev[i + 1]);
+      strncpy(g_prof_names[i], names[i], 31);
+      g_prof_names[i][31] = 0;
+    }
+    for (int i = 0; i <= n; i++) cudaEventDestroy(ev[i]);
+  }
+} // namespace b200
+
 extern "C" {
+
+void b200_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long b200_get_launch_count(void) { return g_launches.load(); }
+void b200_set_profiling(int on) { g_profiling.store(on); }
+int b200_get_last_profile(char* names_out, int names_cap, float* ms_out, int max_stages)
+{
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::string joined = g_prof_what;
+  int k = g_prof_n < max_stages ? g_prof_n : max_stages;
+  for (int i = 0; i < k; i++) {
+    joined += std::string(",") + g_prof_names[i];
+    ms_out[i] = g_prof_ms[i];
+  }
+  if (names_out && names_cap > 0) {
+    strncpy(names_out, joined.c_str(), names_cap - 1);
+    names_out[names_cap - 1] = 0;
+  }
+  return k;
+}
 
 const char* b200_version(void) { return "icicle_b200 0.1 (sm_100a; MSM+NTT+vec-ops; C ABI v1)"; }
 

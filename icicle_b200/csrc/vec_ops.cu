@@ -146,13 +146,13 @@ int vec_op_impl(int op, const void* a, const void* b, uint64_t size, const b200_
   uint32_t* po = (uint32_t*)dout;
   unsigned g = grid_for(n);
   switch (op) {
-  case B200_VEC_ADD: k_vec2<F, B200_VEC_ADD><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, n); break;
-  case B200_VEC_ACCUMULATE: k_vec2<F, B200_VEC_ADD><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, n); break;
-  case B200_VEC_SUB: k_vec2<F, B200_VEC_SUB><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, n); break;
-  case B200_VEC_MUL: k_vec2<F, B200_VEC_MUL><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, n); break;
-  case B200_SCALAR_ADD_VEC: k_scalar_vec<F, B200_SCALAR_ADD_VEC><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, size, batch, cfg->columns_batch); break;
-  case B200_SCALAR_SUB_VEC: k_scalar_vec<F, B200_SCALAR_SUB_VEC><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, size, batch, cfg->columns_batch); break;
-  case B200_SCALAR_MUL_VEC: k_scalar_vec<F, B200_SCALAR_MUL_VEC><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, size, batch, cfg->columns_batch); break;
+  case B200_VEC_ADD: k_vec2<F, B200_VEC_ADD><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, n); B200_LAUNCHED(1); break;
+  case B200_VEC_ACCUMULATE: k_vec2<F, B200_VEC_ADD><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, n); B200_LAUNCHED(1); break;
+  case B200_VEC_SUB: k_vec2<F, B200_VEC_SUB><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, n); B200_LAUNCHED(1); break;
+  case B200_VEC_MUL: k_vec2<F, B200_VEC_MUL><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, n); B200_LAUNCHED(1); break;
+  case B200_SCALAR_ADD_VEC: k_scalar_vec<F, B200_SCALAR_ADD_VEC><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, size, batch, cfg->columns_batch); B200_LAUNCHED(1); break;
+  case B200_SCALAR_SUB_VEC: k_scalar_vec<F, B200_SCALAR_SUB_VEC><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, size, batch, cfg->columns_batch); B200_LAUNCHED(1); break;
+  case B200_SCALAR_MUL_VEC: k_scalar_vec<F, B200_SCALAR_MUL_VEC><<<g, VEC_THREADS, 0, s>>>(pa, pb, po, size, batch, cfg->columns_batch); B200_LAUNCHED(1); break;
   default: return B200_INVALID_ARGUMENT;
   }
   B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
@@ -172,8 +172,11 @@ int convert_mont_impl(const void* in, uint64_t n, int is_into, const b200_vec_op
   if ((err = stage_in(din, in, bytes, cfg->is_a_on_device, s, si))) return err;
   if ((err = stage_out(dout, out, bytes, cfg->is_result_on_device, s, so))) return err;
   unsigned g = grid_for(n);
-  if (is_into) k_convert_mont<F, true><<<g, VEC_THREADS, 0, s>>>((const uint32_t*)din, (uint32_t*)dout, n);
-  else k_convert_mont<F, false><<<g, VEC_THREADS, 0, s>>>((const uint32_t*)din, (uint32_t*)dout, n);
+  if (is_into) {
+    k_convert_mont<F, true><<<g, VEC_THREADS, 0, s>>>((const uint32_t*)din, (uint32_t*)dout, n); B200_LAUNCHED(1);
+  } else {
+    k_convert_mont<F, false><<<g, VEC_THREADS, 0, s>>>((const uint32_t*)din, (uint32_t*)dout, n); B200_LAUNCHED(1);
+  }
   B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
   return finish_out(out, dout, bytes, cfg->is_result_on_device, cfg->is_async, s);
 }
@@ -263,7 +266,7 @@ int b200_bit_reverse(int field, const void* in, uint64_t size, const b200_vec_op
       if ((err = stmp.alloc(bytes, s))) return err;
       target = stmp.p;
     }
-    k_bit_reverse<F><<<grid_for(size * batch), VEC_THREADS, 0, s>>>((const uint32_t*)din, (uint32_t*)target, size, logn, batch, cfg->columns_batch);
+    k_bit_reverse<F><<<grid_for(size * batch), VEC_THREADS, 0, s>>>((const uint32_t*)din, (uint32_t*)target, size, logn, batch, cfg->columns_batch); B200_LAUNCHED(1);
     B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     if (target != dout) B200_CUDA_TRY(cudaMemcpyAsync(dout, target, bytes, cudaMemcpyDeviceToDevice, s), B200_COPY_FAILED);
     return finish_out(out, dout, bytes, cfg->is_result_on_device, cfg->is_async, s);
@@ -294,10 +297,10 @@ int b200_matrix_transpose(int field, const void* in, uint32_t rows, uint32_t col
   }
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
   switch (nw) {
-  case 1: k_transpose<1><<<grid, 256, 0, s>>>((const uint32_t*)din, (uint32_t*)target, rows, cols); break;
-  case 8: k_transpose<8><<<grid, 256, 0, s>>>((const uint32_t*)din, (uint32_t*)target, rows, cols); break;
-  case 12: k_transpose<12><<<grid, 256, 0, s>>>((const uint32_t*)din, (uint32_t*)target, rows, cols); break;
-  case 24: k_transpose<24><<<grid, 256, 0, s>>>((const uint32_t*)din, (uint32_t*)target, rows, cols); break;
+  case 1: k_transpose<1><<<grid, 256, 0, s>>>((const uint32_t*)din, (uint32_t*)target, rows, cols); B200_LAUNCHED(1); break;
+  case 8: k_transpose<8><<<grid, 256, 0, s>>>((const uint32_t*)din, (uint32_t*)target, rows, cols); B200_LAUNCHED(1); break;
+  case 12: k_transpose<12><<<grid, 256, 0, s>>>((const uint32_t*)din, (uint32_t*)target, rows, cols); B200_LAUNCHED(1); break;
+  case 24: k_transpose<24><<<grid, 256, 0, s>>>((const uint32_t*)din, (uint32_t*)target, rows, cols); B200_LAUNCHED(1); break;
   default: return B200_INVALID_ARGUMENT;
   }
   B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
@@ -321,7 +324,7 @@ int b200_slice(int field, const void* in, uint64_t offset, uint64_t stride, uint
     int err;
     if ((err = stage_in(din, in, bytes_in, cfg->is_a_on_device, s, si))) return err;
     if ((err = stage_out(dout, out, bytes_out, cfg->is_result_on_device, s, so))) return err;
-    k_slice<F><<<grid_for(size_out * batch), VEC_THREADS, 0, s>>>((const uint32_t*)din, (uint32_t*)dout, offset, stride, size_in, size_out, batch, cfg->columns_batch);
+    k_slice<F><<<grid_for(size_out * batch), VEC_THREADS, 0, s>>>((const uint32_t*)din, (uint32_t*)dout, offset, stride, size_in, size_out, batch, cfg->columns_batch); B200_LAUNCHED(1);
     B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     return finish_out(out, dout, bytes_out, cfg->is_result_on_device, cfg->is_async, s);
   });

@@ -212,6 +212,19 @@ B200_API int b200_slice(int field, const void* in, uint64_t offset, uint64_t str
 B200_API int b200_affine_convert_montgomery(int curve, const void* in, uint64_t n, int is_into, const b200_vec_ops_config* cfg, void* out);
 B200_API int b200_projective_convert_montgomery(int curve, const void* in, uint64_t n, int is_into, const b200_vec_ops_config* cfg, void* out);
 
+/* out = sum of n homogeneous projective points (standard form).  New capability: the combine step of a point-sharded
+ * multi-GPU MSM after the NCCL all-gather of per-GPU partial results (the reference has no inter-device reduction;
+ * ncclReduce cannot add group elements).  Uses the is_a_on_device / is_result_on_device / stream fields of cfg. */
+B200_API int b200_ec_sum(int curve, const void* points, int n, const b200_vec_ops_config* cfg, void* out);
+
+/* ---- instrumentation (not part of the reference API; used by bench.py and the profiling scripts) ---- */
+/* number of kernels of THIS library launched so far in the process (library kernels such as cub's are not counted) */
+B200_API long long b200_get_launch_count(void);
+/* when on, MSM / NTT calls record CUDA events per stage on the launching stream and synchronise at the end of the call */
+B200_API void b200_set_profiling(int on);
+/* stage timings of the last profiled call: names_out = "what,stage0,stage1,..."; returns the number of stages */
+B200_API int b200_get_last_profile(char* names_out, int names_cap, float* ms_out, int max_stages);
+
 /* library version / build info string (static storage) */
 B200_API const char* b200_version(void);
 

@@ -138,7 +138,8 @@ def test_bn254_batch_and_precompute(ref):
         assert ref.projective_eq(got[b], exp[b])
     # forced chunking of the batch gives the same
     got2 = ib.msm(C, s, P, n, ib.MSMConfig(batch_size=batch, are_points_shared_in_batch=False, ext={"nof_chunks": 3}))
-    assert np.array_equal(got2, got)
+    for b in range(batch):  # same group elements (the projective representative may differ with the chunking)
+        assert ref.projective_eq(got2[b], exp[b])
     # precompute (test_curve_api.cpp:125-171): precompute and msm must agree within a backend; result == plain MSM
     for pf, c in ((2, 0), (3, 7), (8, 4), (5, 16)):
         cfgp = ib.MSMConfig(precompute_factor=pf, c=c)

@@ -1,0 +1,128 @@
+"""CPU suite: pins the oracle.  (1) the C restatement (oracle/port) against the committed golden vectors that were generated
+from the UNMODIFIED reference CPU backend (tools/make_golden.py), (2) when oracle/_ref is present, the port against the
+reference itself on fresh seeded inputs, (3) the reference against first-principles integer arithmetic."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from icicle_b200 import utils
+import common
+import port
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _gold(name):
+    path = os.path.join(GOLD, f"{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"no golden fixture for {name}")
+    return np.load(path)
+
+
+def aff(arr, limbs):
+    pts = common.affine_limbs_to_ints(arr, limbs)
+    return pts[0]
+
+
+@pytest.mark.parametrize("name", ["bn254"])
+def test_port_msm_vs_golden(name):
+    g = _gold(name)
+    cp = utils.curve_params(name)
+    L = utils.field_params(cp["fq"])["limbs"]
+    sl = utils.field_params(cp["fr"])["limbs"]
+    sc = utils.from_limbs(g["msm_scalars"])
+    pts = common.affine_limbs_to_ints(g["msm_points"], L)
+    assert pts[7] is None
+    for c in (4, 9):
+        assert port.msm(name, sc, pts, c=c) == aff(g["msm_result_affine"], L)
+    for bits in (1, 17, 100):
+        assert port.msm(name, sc, pts, c=6, bitsize=bits) == aff(g[f"msm_bitsize{bits}_affine"], L)
+    for b in range(3):
+        assert port.msm(name, sc[b * 32:(b + 1) * 32], pts[:32], c=5) == aff(g["msm_batch3_affine"][b], L)
+    # Montgomery conversion = multiplication by R = 2^(32*limbs)  (fields/params_gen.h:35-50)
+    r = utils.field_params(cp["fr"])["p"]
+    assert utils.from_limbs(g["scalars_montgomery"]) == [s * (1 << (32 * sl)) % r for s in sc]
+
+
+@pytest.mark.parametrize("name,field", [("bn254", "bn254_fr")])
+def test_port_ntt_and_vec_vs_golden(name, field):
+    g = _gold(name)
+    fp = utils.field_params(field)
+    p = fp["p"]
+    logn = 6
+    n = 1 << logn
+    root = utils.from_limbs(g["ntt_root"].reshape(1, -1))[0]
+    w = pow(root, 4, p)  # domain is 2^(logn+2)
+    x = utils.from_limbs(g["ntt_input"])
+    perm = [common.bitrev(i, logn) for i in range(n)]
+    for d in (0, 1):
+        nat = port.ntt(x[:n], w, p, inverse=bool(d))
+        assert nat == utils.from_limbs(g[f"ntt_d{d}_o0"])                                 # kNN
+        assert [nat[perm[i]] for i in range(n)] == utils.from_limbs(g[f"ntt_d{d}_o1"])    # kNR
+        xr = [x[perm[i]] for i in range(n)]                                               # kRN / kRR read bit-reversed input
+        natr = port.ntt(xr, w, p, inverse=bool(d))
+        assert natr == utils.from_limbs(g[f"ntt_d{d}_o2"])
+        assert [natr[perm[i]] for i in range(n)] == utils.from_limbs(g[f"ntt_d{d}_o3"])
+        for kind in ("dom", "arb"):
+            gc = utils.from_limbs(g[f"coset_{kind}"].reshape(1, -1))[0]
+            assert port.ntt(x[:n], w, p, inverse=bool(d), coset=gc) == utils.from_limbs(g[f"ntt_d{d}_coset_{kind}"])
+        cols = utils.from_limbs(g[f"ntt_d{d}_batch2_cols"])
+        for b in range(2):
+            assert port.ntt(x[b::2][:n], w, p, inverse=bool(d)) == cols[b::2]
+    a, b = utils.from_limbs(g["vec_a"]), utils.from_limbs(g["vec_b"])
+    assert port.field_op(field, "add", a, b) == utils.from_limbs(g["vec_add"])
+    assert port.field_op(field, "sub", a, b) == utils.from_limbs(g["vec_sub"])
+    assert port.field_op(field, "mul", a, b) == utils.from_limbs(g["vec_mul"])
+
+
+def test_port_field_arithmetic_all_fields():
+    rng = random.Random(11)
+    for name in utils.PARAMS["fields"]:
+        p = utils.field_params(name)["p"]
+        a = [rng.randrange(p) for _ in range(100)] + [0, p - 1, p - 1]
+        b = [rng.randrange(p) for _ in range(100)] + [0, p - 1, 1]
+        assert port.field_op(name, "mul", a, b) == [x * y % p for x, y in zip(a, b)]
+        assert port.field_op(name, "add", a, b) == [(x + y) % p for x, y in zip(a, b)]
+        assert port.field_op(name, "sub", a, b) == [(x - y) % p for x, y in zip(a, b)]
+
+
+@pytest.mark.parametrize("cname", ["bn254", "grumpkin", "bls12_381", "bls12_377", "bw6_761"])
+def test_port_msm_vs_first_principles(cname):
+    cp = utils.curve_params(cname)
+    q = utils.field_params(cp["fq"])["p"]
+    r = utils.field_params(cp["fr"])["p"]
+    rng = random.Random(5)
+    pts = common.gen_g1_points(cname, 24, 3, as_ints=True)
+    pts[5] = None
+    sc = [rng.randrange(r) for _ in range(24)]
+    sc[0], sc[1] = 0, r - 1
+    assert port.msm(cname, sc, pts, c=7) == common.msm_naive_ints(sc, pts, q)
+    assert port.msm(cname, sc, pts, c=4, bitsize=13) == common.msm_naive_ints([s & 0x1FFF for s in sc], pts, q)
+
+
+def test_port_vs_reference_backend_fresh_inputs():
+    """Same seeded inputs through the real reference (oracle/_ref) and the port."""
+    ref_icicle = pytest.importorskip("ref_icicle")
+    if not ref_icicle.available("bn254"):
+        pytest.skip("oracle/_ref/bn254 not built in this environment")
+    r = ref_icicle.get("bn254")
+    n = 200
+    s, P = r.generate_scalars(n), r.generate_affine_points(n)
+    exp = common.affine_limbs_to_ints(r.to_affine(r.msm(s, P, n)[0]), 8)[0]
+    assert port.msm("bn254", utils.from_limbs(s), common.affine_limbs_to_ints(P, 8), c=8) == exp
+    fp = utils.field_params("bn254_fr")
+    logn = 7
+    root = r.get_root_of_unity(1 << logn)
+    r.ntt_release_domain()
+    r.ntt_init_domain(root)
+    x = r.generate_scalars(1 << logn)
+    w = utils.from_limbs(root.reshape(1, 8))[0]
+    assert port.ntt(utils.from_limbs(x), w, fp["p"]) == utils.from_limbs(r.ntt(x, 1 << logn, 0))
+    assert port.ntt(utils.from_limbs(x), w, fp["p"], inverse=True) == utils.from_limbs(r.ntt(x, 1 << logn, 1))
+    r.ntt_release_domain()
+    # reference vs the defining sum (first principles)
+    xs = utils.from_limbs(x)[:16]
+    w16 = pow(w, 1 << (logn - 4), fp["p"])
+    assert port.ntt(xs, w16, fp["p"]) == common.ntt_naive_ints(xs, w16, fp["p"])
