@@ -5,6 +5,7 @@ torch CUDA tensors (dtype int32/uint8/...; only the pointer is used) -- torch is
 
 Nothing here computes: every function forwards to libicicle_b200.so and raises IcicleError on failure.
 """
+import copy
 import ctypes as C
 import enum
 
@@ -186,7 +187,7 @@ def default_msm_config():
 def msm(curve, scalars, bases, msm_size, config=None, results=None):
     """icicle::msm (icicle/include/icicle/msm.h:93-94 -> src/msm.cpp:12-16).  Returns `results`:
     (batch, 3*coord_limbs) uint32 homogeneous projective points in standard form."""
-    cfg = config or MSMConfig()
+    cfg = copy.copy(config) if config else MSMConfig()
     sp, s_dev, _ks = _ptr(scalars)
     bp, b_dev, _kb = _ptr(bases)
     cfg.are_scalars_on_device = s_dev
@@ -205,7 +206,7 @@ def msm(curve, scalars, bases, msm_size, config=None, results=None):
 
 def msm_precompute_bases(curve, bases, nof_bases, config, output=None):
     """icicle::msm_precompute_bases (msm.h:106-107)."""
-    cfg = config
+    cfg = copy.copy(config)
     bp, b_dev, _kb = _ptr(bases)
     cfg.are_points_on_device = b_dev
     if output is None:
@@ -292,7 +293,7 @@ def get_root_of_unity_from_domain(field, logn):
 
 def ntt(field, input, size, direction, config=None, output=None):
     """icicle::ntt (icicle/include/icicle/ntt.h:108 -> src/ntt.cpp:11-15)."""
-    cfg = config or NTTConfig()
+    cfg = copy.copy(config) if config else NTTConfig()
     ip, i_dev, _ki = _ptr(input)
     cfg.are_inputs_on_device = i_dev
     if output is None:
@@ -342,7 +343,7 @@ def _out_like(field, n_elems, on_device):
 
 
 def _vec2(field, op, a, b, size, config, output):
-    cfg = config or VecOpsConfig()
+    cfg = copy.copy(config) if config else VecOpsConfig()
     ap, a_dev, _ka = _ptr(a)
     bp, b_dev, _kb = _ptr(b)
     cfg.is_a_on_device, cfg.is_b_on_device = a_dev, b_dev
@@ -387,7 +388,7 @@ def scalar_mul_vec(field, scalar_a, b, size, config=None, output=None):
 
 
 def _unary(fn_name, field_or_curve, a, n_out_elems, limbs, config, output, *extra):
-    cfg = config or VecOpsConfig()
+    cfg = copy.copy(config) if config else VecOpsConfig()
     ap, a_dev, _ka = _ptr(a)
     cfg.is_a_on_device = a_dev
     if output is None:

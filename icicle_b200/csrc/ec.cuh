@@ -57,7 +57,7 @@ struct XYZZ {
   }
 
   // 2*this  (EFD "dbl-2008-s-1", a = 0)
-  B200_HD XYZZ dbl() const
+  B200_HD XYZZ dbl_impl() const
   {
     if (is_inf() || y.is_zero()) return inf();
     F U = y.dbl();
@@ -73,7 +73,7 @@ struct XYZZ {
 
   // this += p (affine, Montgomery coordinates).  EFD "madd-2008-s": 8M + 2S.
   // Replaces the reference's mixed add in the bucket hot loop (cpu_msm.hpp:296-304 -> projective.h:147-188).
-  B200_HD void add_affine(const Affine<F>& p)
+  B200_HD void add_affine_impl(const Affine<F>& p)
   {
     if (p.is_zero()) return; // reference skips zero bases: cpu_msm.hpp:282
     if (is_inf()) {
@@ -100,7 +100,7 @@ struct XYZZ {
   }
 
   // this += o.  EFD "add-2008-s": 12M + 2S.
-  B200_HD void add(const XYZZ& o)
+  B200_HD void add_impl(const XYZZ& o)
   {
     if (o.is_inf()) return;
     if (is_inf()) { *this = o; return; }
@@ -111,7 +111,7 @@ struct XYZZ {
     F P = U2 - U1;
     F R = S2 - S1;
     if (P.is_zero()) {
-      if (R.is_zero()) *this = dbl();
+      if (R.is_zero()) *this = dbl_impl();
       else *this = inf();
       return;
     }
@@ -123,6 +123,39 @@ struct XYZZ {
     x = X3; y = Y3;
     zz = zz * o.zz * PP;
     zzz = zzz * o.zzz * PPP;
+  }
+
+
+  // For fields wider than 256 bits (and for Fq2) one group operation is 5-15 thousand SASS instructions; inlining it at
+  // every call site makes kernels that ptxas needs tens of minutes for and that thrash the instruction cache.  Those
+  // instantiations call the operation out of line (the operands then live in local memory across the call, a few hundred
+  // bytes against thousands of multiply instructions); the 256-bit G1 hot path stays fully inlined.
+  static constexpr bool kOutOfLine = (F::BYTES > 32);
+#ifdef __CUDACC__
+  __device__ __noinline__ void add_affine_ool(const Affine<F>& p) { add_affine_impl(p); }
+  __device__ __noinline__ void add_ool(const XYZZ& o) { add_impl(o); }
+  __device__ __noinline__ XYZZ dbl_ool() const { return dbl_impl(); }
+#endif
+  B200_HD void add_affine(const Affine<F>& p)
+  {
+#ifdef __CUDA_ARCH__
+    if constexpr (kOutOfLine) { add_affine_ool(p); return; }
+#endif
+    add_affine_impl(p);
+  }
+  B200_HD void add(const XYZZ& o)
+  {
+#ifdef __CUDA_ARCH__
+    if constexpr (kOutOfLine) { add_ool(o); return; }
+#endif
+    add_impl(o);
+  }
+  B200_HD XYZZ dbl() const
+  {
+#ifdef __CUDA_ARCH__
+    if constexpr (kOutOfLine) return dbl_ool();
+#endif
+    return dbl_impl();
   }
 
   // homogeneous projective representative (X*ZZZ : Y*ZZ : ZZ*ZZZ), Montgomery coordinates; infinity -> (0,1,0)

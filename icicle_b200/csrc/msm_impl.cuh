@@ -357,7 +357,14 @@ __device__ Fp<P> inv_fp(const Fp<P>& a)
   uint32_t e[B::N];
 #pragma unroll
   for (int i = 0; i < B::N; i++) e[i] = P::p(i);
-  e[0] -= 2;
+  { // e = p - 2 with borrow propagation (several moduli end in ...00000001)
+    uint32_t borrow = 2;
+    for (int i = 0; i < (int)(sizeof(e) / sizeof(e[0])) && borrow; i++) {
+      uint32_t before = e[i];
+      e[i] = before - borrow;
+      borrow = (before < borrow) ? 1u : 0u;
+    }
+  }
   B r = B::one();
   for (int i = B::N * 32 - 1; i >= 0; i--) {
     r = r * r;

@@ -68,7 +68,14 @@ __device__ F inv_dev(const F& a_m)
   uint32_t e[F::N];
 #pragma unroll
   for (int i = 0; i < F::N; i++) e[i] = F::P::p(i);
-  e[0] -= 2; // p is odd and > 2, no borrow
+  { // e = p - 2 with borrow propagation (several moduli end in ...00000001)
+    uint32_t borrow = 2;
+    for (int i = 0; i < (int)(sizeof(e) / sizeof(e[0])) && borrow; i++) {
+      uint32_t before = e[i];
+      e[i] = before - borrow;
+      borrow = (before < borrow) ? 1u : 0u;
+    }
+  }
   F r = F::one();
   for (int i = F::N * 32 - 1; i >= 0; i--) {
     r = r * r;

@@ -114,7 +114,7 @@ def test_vs_reference_randomized(domains):
         got = ib.to_host(d_out, x.shape)
         assert np.array_equal(got, exp), dict(trial=trial, logn=logn, batch=batch, columns=columns, inplace=inplace, dir=direction, ordering=ordering, coset=coset_kind)
         # host-memory path gives the same
-        got_h = ib.ntt(field, x, n, direction, cfg)
+        got_h = ib.ntt(field, x, n, direction, ib.NTTConfig(coset_gen=coset, batch_size=batch, columns_batch=columns, ordering=ib.Ordering(ordering)))
         assert np.array_equal(got_h, exp)
     r.ntt_release_domain()
 

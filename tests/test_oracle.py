@@ -126,3 +126,22 @@ def test_port_vs_reference_backend_fresh_inputs():
     xs = utils.from_limbs(x)[:16]
     w16 = pow(w, 1 << (logn - 4), fp["p"])
     assert port.ntt(xs, w16, fp["p"]) == common.ntt_naive_ints(xs, w16, fp["p"])
+
+
+def test_port_vs_golden_other_curves():
+    """bls12_381 (G1 MSM + Fr NTT) and babybear (NTT) fixtures generated from their reference builds."""
+    g = _gold("bls12_381")
+    sc = utils.from_limbs(g["msm_scalars"])
+    pts = common.affine_limbs_to_ints(g["msm_points"], 12)
+    assert port.msm("bls12_381", sc, pts, c=7) == aff(g["msm_result_affine"], 12)
+    for name, field in (("bls12_381", "bls12_381_fr"), ("babybear", "babybear")):
+        g = _gold(name)
+        fp = utils.field_params(field)
+        L = fp["limbs"]
+        root = utils.from_limbs(g["ntt_root"].reshape(1, -1))[0]
+        w = pow(root, 4, fp["p"])
+        x = utils.from_limbs(g["ntt_input"].reshape(-1, L))
+        for d in (0, 1):
+            assert port.ntt(x[:64], w, fp["p"], inverse=bool(d), field_name=field) == utils.from_limbs(g[f"ntt_d{d}_o0"].reshape(-1, L))
+            gc = utils.from_limbs(g["coset_arb"].reshape(1, -1))[0]
+            assert port.ntt(x[:64], w, fp["p"], inverse=bool(d), coset=gc, field_name=field) == utils.from_limbs(g[f"ntt_d{d}_coset_arb"].reshape(-1, L))

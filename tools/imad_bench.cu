@@ -29,6 +29,22 @@ __global__ void __launch_bounds__(256) k_pipe(uint32_t* out, uint32_t seed, int 
         madc_wide_cc(a2, b2, a3, x);
         madc_wide_cc(a1, b1, a0, x);
         madc_wide_cc(a3, b3, a2, x);
+      } else if (MODE == 4) { // 4 independent DFMA chains (FP64 pipe)
+        double d0 = __longlong_as_double(((long long)b0 << 32) | a0), d1 = __longlong_as_double(((long long)b1 << 32) | a1);
+        double d2 = __longlong_as_double(((long long)b2 << 32) | a2), d3 = __longlong_as_double(((long long)b3 << 32) | a3);
+        const double m = 1.0000001, c = 1e-9;
+        d0 = fma(d0, m, c); d1 = fma(d1, m, c); d2 = fma(d2, m, c); d3 = fma(d3, m, c);
+        long long l0 = __double_as_longlong(d0), l1 = __double_as_longlong(d1), l2 = __double_as_longlong(d2), l3 = __double_as_longlong(d3);
+        a0 = (uint32_t)l0; b0 = (uint32_t)(l0 >> 32); a1 = (uint32_t)l1; b1 = (uint32_t)(l1 >> 32);
+        a2 = (uint32_t)l2; b2 = (uint32_t)(l2 >> 32); a3 = (uint32_t)l3; b3 = (uint32_t)(l3 >> 32);
+      } else if (MODE == 5) { // 2 DFMA chains + 2 carry-chained IMAD.WIDE.X: do the two pipes run concurrently?
+        double d0 = __longlong_as_double(((long long)b0 << 32) | a0), d1 = __longlong_as_double(((long long)b1 << 32) | a1);
+        const double m = 1.0000001, c = 1e-9;
+        d0 = fma(d0, m, c); d1 = fma(d1, m, c);
+        long long l0 = __double_as_longlong(d0), l1 = __double_as_longlong(d1);
+        a0 = (uint32_t)l0; b0 = (uint32_t)(l0 >> 32); a1 = (uint32_t)l1; b1 = (uint32_t)(l1 >> 32);
+        mad_wide_cc(a2, b2, a3, x);
+        madc_wide_cc(a3, b3, a2, x);
       } else { // IADD3 chains
         a0 = a0 + b0 + x; a1 = a1 + b1 + x; a2 = a2 + b2 + x; a3 = a3 + b3 + x;
         b0 ^= a1; b1 ^= a2; b2 ^= a3; b3 ^= a0;
@@ -85,6 +101,10 @@ int main()
   printf("%-34s %8.1f G thread-instr/s  (%.3f ms)\n", names[1], n_thread_instr / ms / 1e6, ms);
   ms = time_ms([&] { k_pipe<2><<<blocks, threads>>>(out, 1, iters); });
   printf("%-34s %8.1f G thread-instr/s  (%.3f ms)\n", names[2], n_thread_instr / ms / 1e6, ms);
+  ms = time_ms([&] { k_pipe<4><<<blocks, threads>>>(out, 1, iters); });
+  printf("%-34s %8.1f G thread-instr/s  (%.3f ms)\n", "DFMA (FP64)", n_thread_instr / ms / 1e6, ms);
+  ms = time_ms([&] { k_pipe<5><<<blocks, threads>>>(out, 1, iters); });
+  printf("%-34s %8.1f G thread-instr/s  (%.3f ms; 2 DFMA + 2 IMAD.WIDE.X per counted group of 4)\n", "DFMA + IMAD.WIDE.X mixed", n_thread_instr / ms / 1e6, ms);
   ms = time_ms([&] { k_pipe<3><<<blocks, threads>>>(out, 1, iters); });
   printf("%-34s %8.1f G thread-instr/s  (%.3f ms, 2 instr per counted op)\n", names[3], 2 * n_thread_instr / ms / 1e6, ms);
   {
