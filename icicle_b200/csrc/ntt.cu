@@ -18,6 +18,8 @@
 // (forward) and the N^-1 * g^-i scaling into the last pass (inverse).
 // Algorithmic bytes: 2*|E| per element per transform (one read + one write); this schedule moves ceil(n/4) times that.
 #include "common.cuh"
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -192,19 +194,25 @@ __global__ void __launch_bounds__(128) k_ntt_pass(const uint32_t* __restrict__ s
     const uint32_t s = lo + t;
     const uint32_t sh = p.dom_log - (s + 1);
     const bool trivial = (s == 0); // twiddle exponent is always 0 in the last stage
+    // butterflies (m, m + 2^t) with the same j = m mod 2^t share one twiddle: load it once, use it 2^(LOGR-1-t) times
 #pragma unroll
-    for (int m = 0; m < R; m++) {
-      if (m & (1 << t)) continue;
-      const int m2 = m | (1 << t);
-      F u = e[m], v = e[m2];
-      e[m] = u + v;
-      F d = u - v;
+    for (int j = 0; j < (1 << t); j++) {
+      F w;
       if (!trivial) {
-        uint64_t ex = ((((uint64_t)(m & ((1 << t) - 1))) << lo) | low) << sh;
+        uint64_t ex = ((((uint64_t)j) << lo) | low) << sh;
         if (p.inverse) ex = (0 - ex) & dom_mask;
-        d = d * load_fp<F>(p.tw + ex * F::N);
+        w = load_fp<F>(p.tw + ex * F::N);
       }
-      e[m2] = d;
+#pragma unroll
+      for (int g = 0; g < (R >> (t + 1)); g++) {
+        const int m = (g << (t + 1)) | j;
+        const int m2 = m | (1 << t);
+        F u = e[m], v = e[m2];
+        e[m] = u + v;
+        F d = u - v;
+        if (!trivial) d = d * w;
+        e[m2] = d;
+      }
     }
   }
 
@@ -220,6 +228,201 @@ __global__ void __launch_bounds__(128) k_ntt_pass(const uint32_t* __restrict__ s
     }
     store_fp<F>(dst + (boff + idx * p.estride) * F::N, e[m]);
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// v2 pass: shared-memory tile.  One CTA (256 threads) transforms a tile of 2048 elements = C columns x 2^S strided rows
+// (C = 2^(11-S)), S = 5..9 DIF stages per pass, as rounds of <= 3 stages kept in registers (8 elements per thread) with
+// the tile exchanged through shared memory between rounds.  A 2^24 transform is 3 HBM round trips (8+8+8 stages).
+// Shared memory holds the tile limb-major ([limb][element], padded by one word per 32 elements): a warp reads one limb
+// of 32 consecutive elements per LDS, so the round-to-round exchange is bank-conflict-free in the long-stride rounds and
+// at most 4-way conflicted in the short last round -- far below the IMAD.WIDE time of the 12 Montgomery products a
+// thread does per round.  Twiddles come from the Montgomery-form domain table (7 loads per 8-element radix-8 group).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TILE_LOG = 11;
+constexpr int TILE = 1 << TILE_LOG;
+constexpr int TILE_PAD = TILE + TILE / 32;
+
+__device__ __forceinline__ uint32_t tile_slot(uint32_t e) { return e + (e >> 5); }
+
+template <class F>
+__device__ __forceinline__ F tile_load(const uint32_t* sm, uint32_t e)
+{
+  F r;
+  const uint32_t s = tile_slot(e);
+#pragma unroll
+  for (int i = 0; i < F::N; i++) r.v[i] = sm[i * TILE_PAD + s];
+  return r;
+}
+template <class F>
+__device__ __forceinline__ void tile_store(uint32_t* sm, uint32_t e, const F& a)
+{
+  const uint32_t s = tile_slot(e);
+#pragma unroll
+  for (int i = 0; i < F::N; i++) sm[i * TILE_PAD + s] = a.v[i];
+}
+
+// Q DIF stages (local stages [a, a+Q)) on the 8 register-resident elements of this thread: 2^(3-Q) groups of 2^Q.
+// jbase[grp] = (m mod 2^a) of the group's elements (bits of m below the round), low/lo/dom as in the v1 pass.
+template <class F, int Q>
+__device__ __forceinline__ void tile_round(F (&e)[8], const PassParams& p, uint32_t a, const uint32_t (&mlo)[8 >> Q], const uint64_t (&low)[8 >> Q])
+{
+  constexpr int G = 8 >> Q;
+  const uint64_t dom_mask = (1ull << p.dom_log) - 1;
+#pragma unroll
+  for (int i = Q - 1; i >= 0; --i) {
+    const uint32_t s = p.lo + a + i; // global stage
+    const uint32_t sh = p.dom_log - (s + 1);
+    const bool trivial = (s == 0);
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+#pragma unroll
+      for (int kk = 0; kk < (1 << i); kk++) {
+        F w;
+        if (!trivial) {
+          const uint64_t j = ((uint64_t)kk << a) | mlo[g]; // m mod 2^(a+i)
+          uint64_t ex = ((j << p.lo) | low[g]) << sh;
+          if (p.inverse) ex = (0 - ex) & dom_mask;
+          w = load_fp<F>(p.tw + ex * F::N);
+        }
+#pragma unroll
+        for (int up = 0; up < (1 << (Q - 1 - i)); up++) {
+          const int k0 = (up << (i + 1)) | kk, k1 = k0 | (1 << i);
+          F u = e[g * (1 << Q) + k0], v = e[g * (1 << Q) + k1];
+          e[g * (1 << Q) + k0] = u + v;
+          F d = u - v;
+          if (!trivial) d = d * w;
+          e[g * (1 << Q) + k1] = d;
+        }
+      }
+    }
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(256, 2) k_ntt_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassParams p, uint32_t S, uint64_t total_cols)
+{
+  extern __shared__ uint32_t sm[];
+  const uint32_t T = threadIdx.x;
+  const uint32_t logC = TILE_LOG - S, C = 1u << logC;
+  const uint32_t lo = p.lo, n_log = p.n_log;
+  const uint32_t rev_shift = 64 - n_log;
+  const uint64_t ntt_mask = (1ull << n_log) - 1;
+  const uint64_t col0 = (uint64_t)blockIdx.x * C;
+
+  F e[8];
+  int a = (int)S;
+  bool first_round = true;
+  while (a > 0) {
+    const int q = (a >= 3) ? 3 : a;
+    a -= q;
+    const bool last_round = (a == 0);
+    const uint32_t P = (uint32_t)a + logC;
+    uint32_t eid[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const uint32_t k = u & ((1u << q) - 1), grp = u >> q;
+      const uint32_t rest = T + 256u * grp;
+      eid[u] = ((rest >> P) << (P + q)) | (k << P) | (rest & ((1u << P) - 1));
+    }
+    // ---- load ----
+    if (first_round) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const uint32_t m = eid[u] >> logC, c = eid[u] & (C - 1);
+        const uint64_t colg = col0 + c;
+        if (colg < total_cols) {
+          const uint64_t pos = ((colg >> lo) << (lo + S)) | ((uint64_t)m << lo) | (colg & ((1ull << lo) - 1)); // position incl. batch
+          const uint64_t pin = pos & ntt_mask;                                                                   // position inside its NTT
+          uint64_t idx = pos;
+          if (p.first && p.gather_in) idx = (pos & ~ntt_mask) | (__brevll(pin) >> rev_shift);
+          e[u] = load_fp<F>(src + idx * F::N);
+          if (p.in_mul) e[u] = e[u] * load_fp<F>(p.in_mul + pin * F::N);
+        } else {
+          e[u] = F::zero();
+        }
+      }
+    } else {
+      __syncthreads(); // previous round's stores are visible
+#pragma unroll
+      for (int u = 0; u < 8; u++) e[u] = tile_load<F>(sm, eid[u]);
+      __syncthreads(); // everyone has read before anyone overwrites
+    }
+    // ---- butterflies ----
+    {
+      // per group: m_lo (bits of m below the round) and the column's low index
+      uint32_t mlo[8];
+      uint64_t lowv[8];
+#pragma unroll
+      for (int g = 0; g < 8; g++) {
+        // group g of this round starts at element u = g << q (only the first 8>>q entries are used)
+        const int u = (g << q) & 7;
+        const uint32_t m = eid[u] >> logC, c = eid[u] & (C - 1);
+        mlo[g] = m & ((1u << a) - 1);
+        lowv[g] = (col0 + c) & ((1ull << lo) - 1);
+      }
+      if (q == 3) {
+        const uint32_t m1[1] = {mlo[0]};
+        const uint64_t l1[1] = {lowv[0]};
+        tile_round<F, 3>(e, p, (uint32_t)a, m1, l1);
+      } else if (q == 2) {
+        const uint32_t m2[2] = {mlo[0], mlo[1]};
+        const uint64_t l2[2] = {lowv[0], lowv[1]};
+        tile_round<F, 2>(e, p, (uint32_t)a, m2, l2);
+      } else {
+        const uint32_t m4[4] = {mlo[0], mlo[1], mlo[2], mlo[3]};
+        const uint64_t l4[4] = {lowv[0], lowv[1], lowv[2], lowv[3]};
+        tile_round<F, 1>(e, p, (uint32_t)a, m4, l4);
+      }
+    }
+    // ---- store ----
+    if (last_round) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const uint32_t m = eid[u] >> logC, c = eid[u] & (C - 1);
+        const uint64_t colg = col0 + c;
+        if (colg >= total_cols) continue;
+        const uint64_t pos = ((colg >> lo) << (lo + S)) | ((uint64_t)m << lo) | (colg & ((1ull << lo) - 1));
+        const uint64_t pin = pos & ntt_mask;
+        uint64_t idx = pos;
+        if (p.last) {
+          const uint64_t kidx = n_log ? (__brevll(pin) >> rev_shift) : 0; // logical output index held at this position
+          if (p.out_mul) e[u] = e[u] * load_fp<F>(p.out_mul + kidx * F::N);
+          else if (p.out_scale) e[u] = e[u] * load_fp<F>(p.out_scale);
+          if (p.scatter_out) idx = (pos & ~ntt_mask) | kidx;
+        }
+        store_fp<F>(dst + idx * F::N, e[u]);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; u++) tile_store<F>(sm, eid[u], e[u]);
+    }
+    first_round = false;
+  }
+}
+
+template <class F>
+int launch_tile_pass(const uint32_t* src, uint32_t* dst, const PassParams& p, int S, cudaStream_t s)
+{
+  const uint64_t total = ((uint64_t)1 << p.n_log) * p.batch;
+  const uint64_t total_cols = total >> S;
+  const uint32_t C = 1u << (TILE_LOG - S);
+  const uint64_t blocks = (total_cols + C - 1) / C;
+  const size_t smem = (size_t)TILE_PAD * F::N * 4;
+  B200_CUDA_TRY(cudaFuncSetAttribute(k_ntt_tile<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), B200_UNKNOWN_ERROR);
+  k_ntt_tile<F><<<(unsigned)blocks, 256, smem, s>>>(src, dst, p, (uint32_t)S, total_cols); B200_LAUNCHED(1);
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  return B200_SUCCESS;
+}
+
+// split n_log stages into tile passes of 5..9 stages (as few passes as possible, sizes as even as possible)
+int plan_tile_passes(int n_log, int* S)
+{
+  int k = (n_log + 8) / 9;
+  int basev = n_log / k, extra = n_log % k;
+  for (int i = 0; i < k; i++) S[i] = basev + (i < extra ? 1 : 0);
+  return k;
 }
 
 template <class F, int LOGR>
@@ -370,9 +573,14 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
   }
 
   // ---- pass schedule ---------------------------------------------------------------------------------------------------
+  // Mixed-radix tile passes (v2) for row-major batches with at least one full tile and fields that fit the tile in shared
+  // memory; register-only radix-2^k passes (v1) otherwise, and always when the caller asks for Radix2.
   int maxr = (cfg->ext_ntt_algorithm == B200_NTT_ALG_RADIX2) ? 1 : (F::N >= 12 ? 3 : 4);
+  if (const char* ev = getenv("B200_NTT_MAXR")) maxr = std::max(1, std::min(4, atoi(ev)));
+  bool use_tiles = (cfg->ext_ntt_algorithm != B200_NTT_ALG_RADIX2) && !cfg->columns_batch && n_log >= 5 && total >= (uint64_t)TILE && F::N <= 12;
+  if (const char* ev = getenv("B200_NTT_TILES")) use_tiles = use_tiles && atoi(ev) != 0;
   int radices[32];
-  const int npass = plan_passes(n_log, maxr, radices);
+  const int npass = use_tiles ? plan_tile_passes(n_log, radices) : plan_passes(n_log, maxr, radices);
 
   // working buffer: see the header comment of this file for the in-place rules
   const bool need_tmp = scatter_out || (gather_in && din == dout) || (npass == 1 && din == dout && (gather_in || scatter_out));
@@ -420,7 +628,11 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
     } else {
       dstp = work;
     }
-    if ((err = launch_pass_r<F>(r, src, dstp, p, s))) return err;
+    if (use_tiles) {
+      if ((err = launch_tile_pass<F>(src, dstp, p, r, s))) return err;
+    } else if ((err = launch_pass_r<F>(r, src, dstp, p, s))) {
+      return err;
+    }
     prof.mark("pass");
     src = dstp;
     hi -= r;
