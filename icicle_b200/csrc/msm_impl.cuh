@@ -27,6 +27,7 @@
 #pragma once
 #include "common.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 
@@ -468,45 +469,16 @@ MsmPlan make_plan(int msm_size, const b200_msm_config* cfg)
   return pl;
 }
 
+// Device-resident core: scalars (standard or Montgomery form), points already in Montgomery form, results written to d_res
+// (device).  Everything is enqueued on `s`; nothing here synchronises.
 template <class C>
-int msm_impl(const void* scalars, const void* bases, int msm_size, const b200_msm_config* cfg, void* results)
+int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPlan& pl, int batch, bool shared, const b200_msm_config* cfg,
+             void* d_res, cudaStream_t s, StageTimer& prof)
 {
   typedef typename C::Scalar S;
   typedef typename C::Base F;
-  typedef typename base_fp<F>::type B;
   constexpr int AW = 2 * F::N, XW = 4 * F::N, PW = 3 * F::N;
-  cudaStream_t s = (cudaStream_t)cfg->stream;
-  const int batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
-  if (msm_size <= 0) return B200_INVALID_ARGUMENT;
-  const MsmPlan pl = make_plan<C>(msm_size, cfg);
-  const uint32_t n = (uint32_t)msm_size;
-  const bool shared = cfg->are_points_shared_in_batch || batch == 1;
-  const uint64_t n_points = (uint64_t)n * pl.pf * (shared ? 1 : batch);
   int err;
-
-  // ---- inputs --------------------------------------------------------------------------------------------------------
-  Scratch s_scal, s_pts, s_pts_m, s_res;
-  const void *d_scal, *d_pts;
-  void* d_res;
-  if ((err = stage_in(d_scal, scalars, (size_t)n * batch * S::BYTES, cfg->are_scalars_on_device, s, s_scal))) return err;
-  if ((err = stage_in(d_pts, bases, (size_t)n_points * AW * 4, cfg->are_points_on_device, s, s_pts))) return err;
-  if ((err = stage_out(d_res, results, (size_t)batch * PW * 4, cfg->are_results_on_device, s, s_res))) return err;
-  const uint32_t* pts_m = (const uint32_t*)d_pts;
-  if (!cfg->are_points_montgomery_form) {
-    uint32_t* dst;
-    if (!cfg->are_points_on_device) {
-      dst = s_pts.as<uint32_t>(); // our own staging copy: convert in place
-    } else {
-      if ((err = s_pts_m.alloc((size_t)n_points * AW * 4, s))) return err;
-      dst = s_pts_m.as<uint32_t>();
-    }
-    const uint64_t ncoord = n_points * 2 * (F::N / B::N);
-    unsigned g = (unsigned)std::min<uint64_t>((ncoord + 255) / 256, (uint64_t)num_sms() * 16);
-    k_to_mont<B><<<g, 256, 0, s>>>((const uint32_t*)d_pts, dst, ncoord); B200_LAUNCHED(1);
-    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
-    pts_m = dst;
-  }
-
   // ---- batch chunking so that entry counts fit 31 bits and memory stays bounded ----------------------------------------
   const uint64_t ent_per_msm = (uint64_t)n * pl.nwin;
   uint64_t max_entries = 1ull << 30;
@@ -555,8 +527,6 @@ int msm_impl(const void* scalars, const void* bases, int msm_size, const b200_ms
   if ((err = s_red0.alloc(std::max<uint64_t>(max_chunks, 1) * XW * 4, s))) return err;
   if ((err = s_red1.alloc(std::max<uint64_t>(max_chunks / 2 + 1, 1) * XW * 4, s))) return err;
 
-  StageTimer prof;
-  prof.begin(s);
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int bl = std::min(chunk, batch - b0);
     const uint64_t n_ent = ent_per_msm * bl;
@@ -630,6 +600,144 @@ int msm_impl(const void* scalars, const void* bases, int msm_size, const b200_ms
     k_final<F><<<(bl + 31) / 32, 32, 0, s>>>(cur, (uint32_t)pl.nbm, (uint32_t)pl.c, (uint32_t)bl, (uint32_t*)d_res + (uint64_t)b0 * PW); B200_LAUNCHED(1);
     B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
   }
+  return B200_SUCCESS;
+}
+
+template <class F>
+__global__ void k_proj_sum(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out);
+
+// Host-pointer fast path (the reference-facing call with HOST scalars and points, i.e. what `e2e` measures): the MSM is cut into
+// point-range chunks; chunk i+1 is copied host->device on a private copy stream while chunk i runs on the caller's stream
+// (double-buffered staging, events in both directions), and the per-chunk partial results are summed by k_proj_sum.
+// PCIe (~55 GB/s) moves 96 B/point, so a 2^26 MSM is transfer-bound unless the copies hide behind the arithmetic.
+inline cudaStream_t copy_stream_for_current_device()
+{
+  static thread_local cudaStream_t streams[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!streams[dev]) cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking);
+  return streams[dev];
+}
+
+template <class C>
+int msm_pipelined(const void* scalars, const void* bases, uint32_t n, const b200_msm_config* cfg, void* results)
+{
+  typedef typename C::Scalar S;
+  typedef typename C::Base F;
+  typedef typename base_fp<F>::type B;
+  constexpr int AW = 2 * F::N, PW = 3 * F::N;
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  cudaStream_t cs = copy_stream_for_current_device();
+  if (!cs) return B200_UNKNOWN_ERROR;
+  const uint32_t pf = cfg->precompute_factor > 0 ? cfg->precompute_factor : 1;
+  uint32_t chunk = 1u << 22;
+  while ((uint64_t)chunk * 4 < n) chunk <<= 1; // at most 4..8 chunks
+  const uint32_t nchunks = (n + chunk - 1) / chunk;
+  int err;
+  Scratch d_s[2], d_p[2], d_part, s_res;
+  for (int b = 0; b < 2; b++) {
+    if ((err = d_s[b].alloc((size_t)chunk * S::BYTES, s))) return err;
+    if ((err = d_p[b].alloc((size_t)chunk * pf * AW * 4, s))) return err;
+  }
+  if ((err = d_part.alloc((size_t)nchunks * PW * 4, s))) return err;
+  void* d_res;
+  if ((err = stage_out(d_res, results, (size_t)PW * 4, cfg->are_results_on_device, s, s_res))) return err;
+  cudaEvent_t ready, copied[2], consumed[2];
+  cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+  for (int b = 0; b < 2; b++) {
+    cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming);
+  }
+  cudaEventRecord(ready, s); // staging buffers exist (stream-ordered allocation) and earlier work on s is ordered before the copies
+  cudaStreamWaitEvent(cs, ready, 0);
+  StageTimer prof;
+  prof.begin(s);
+  int rc = B200_SUCCESS;
+  for (uint32_t i = 0; i < nchunks && rc == B200_SUCCESS; i++) {
+    const int b = i & 1;
+    const uint32_t off = i * chunk;
+    const uint32_t cn = (n - off < chunk) ? (n - off) : chunk;
+    if (i >= 2) cudaStreamWaitEvent(cs, consumed[b], 0);
+    cudaMemcpyAsync(d_s[b].p, (const uint8_t*)scalars + (size_t)off * S::BYTES, (size_t)cn * S::BYTES, cudaMemcpyHostToDevice, cs);
+    cudaMemcpyAsync(d_p[b].p, (const uint8_t*)bases + (size_t)off * pf * AW * 4, (size_t)cn * pf * AW * 4, cudaMemcpyHostToDevice, cs);
+    cudaEventRecord(copied[b], cs);
+    cudaStreamWaitEvent(s, copied[b], 0);
+    if (!cfg->are_points_montgomery_form) {
+      const uint64_t ncoord = (uint64_t)cn * pf * 2 * (F::N / B::N);
+      unsigned g = (unsigned)std::min<uint64_t>((ncoord + 255) / 256, (uint64_t)num_sms() * 16);
+      k_to_mont<B><<<g, 256, 0, s>>>(d_p[b].as<uint32_t>(), d_p[b].as<uint32_t>(), ncoord); B200_LAUNCHED(1);
+    }
+    b200_msm_config sub = *cfg;
+    sub.batch_size = 1;
+    const MsmPlan pl = make_plan<C>((int)cn, &sub);
+    rc = msm_core<C>(d_s[b].p, d_p[b].as<uint32_t>(), cn, pl, 1, true, &sub, d_part.as<uint32_t>() + (size_t)i * PW, s, prof);
+    cudaEventRecord(consumed[b], s);
+  }
+  if (rc == B200_SUCCESS) {
+    k_proj_sum<F><<<1, 32, 0, s>>>(d_part.as<uint32_t>(), nchunks, (uint32_t*)d_res); B200_LAUNCHED(1);
+    if (cudaGetLastError() != cudaSuccess) rc = B200_UNKNOWN_ERROR;
+  }
+  prof.mark("final");
+  prof.finish("msm_pipelined");
+  if (rc == B200_SUCCESS) rc = finish_out(results, d_res, (size_t)PW * 4, cfg->are_results_on_device, cfg->is_async, s);
+  if (rc != B200_SUCCESS) {
+    cudaStreamSynchronize(cs);
+    cudaStreamSynchronize(s);
+  }
+  cudaEventDestroy(ready);
+  for (int b = 0; b < 2; b++) {
+    cudaEventDestroy(copied[b]);
+    cudaEventDestroy(consumed[b]);
+  }
+  return rc;
+}
+
+template <class C>
+int msm_impl(const void* scalars, const void* bases, int msm_size, const b200_msm_config* cfg, void* results)
+{
+  typedef typename C::Scalar S;
+  typedef typename C::Base F;
+  typedef typename base_fp<F>::type B;
+  constexpr int AW = 2 * F::N, XW = 4 * F::N, PW = 3 * F::N;
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  const int batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
+  if (msm_size <= 0) return B200_INVALID_ARGUMENT;
+  if (batch == 1 && !cfg->are_scalars_on_device && !cfg->are_points_on_device && (uint32_t)msm_size >= (1u << 23) &&
+      (uint64_t)msm_size * (cfg->precompute_factor > 0 ? cfg->precompute_factor : 1) < (1ull << 31) && !getenv("B200_MSM_NO_PIPELINE"))
+    return msm_pipelined<C>(scalars, bases, (uint32_t)msm_size, cfg, results);
+  const MsmPlan pl = make_plan<C>(msm_size, cfg);
+  const uint32_t n = (uint32_t)msm_size;
+  const bool shared = cfg->are_points_shared_in_batch || batch == 1;
+  const uint64_t n_points = (uint64_t)n * pl.pf * (shared ? 1 : batch);
+  int err;
+
+  // ---- inputs --------------------------------------------------------------------------------------------------------
+  Scratch s_scal, s_pts, s_pts_m, s_res;
+  const void *d_scal, *d_pts;
+  void* d_res;
+  if ((err = stage_in(d_scal, scalars, (size_t)n * batch * S::BYTES, cfg->are_scalars_on_device, s, s_scal))) return err;
+  if ((err = stage_in(d_pts, bases, (size_t)n_points * AW * 4, cfg->are_points_on_device, s, s_pts))) return err;
+  if ((err = stage_out(d_res, results, (size_t)batch * PW * 4, cfg->are_results_on_device, s, s_res))) return err;
+  const uint32_t* pts_m = (const uint32_t*)d_pts;
+  if (!cfg->are_points_montgomery_form) {
+    uint32_t* dst;
+    if (!cfg->are_points_on_device) {
+      dst = s_pts.as<uint32_t>(); // our own staging copy: convert in place
+    } else {
+      if ((err = s_pts_m.alloc((size_t)n_points * AW * 4, s))) return err;
+      dst = s_pts_m.as<uint32_t>();
+    }
+    const uint64_t ncoord = n_points * 2 * (F::N / B::N);
+    unsigned g = (unsigned)std::min<uint64_t>((ncoord + 255) / 256, (uint64_t)num_sms() * 16);
+    k_to_mont<B><<<g, 256, 0, s>>>((const uint32_t*)d_pts, dst, ncoord); B200_LAUNCHED(1);
+    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    pts_m = dst;
+  }
+
+  StageTimer prof;
+  prof.begin(s);
+  if ((err = msm_core<C>(d_scal, pts_m, n, pl, batch, shared, cfg, d_res, s, prof))) return err;
   prof.mark("final");
   prof.finish("msm");
   return finish_out(results, d_res, (size_t)batch * PW * 4, cfg->are_results_on_device, cfg->is_async, s);

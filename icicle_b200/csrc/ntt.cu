@@ -49,6 +49,8 @@ struct PassParams {
   uint64_t bstride, estride; // element strides: addr(b, i) = b*bstride + i*estride
   uint32_t n_log, lo, dom_log, batch;
   uint8_t inverse, gather_in, scatter_out, columns, first, last;
+  uint8_t rot;   // tile passes only: autosort schedule (transformed digit is written bit-reversed below the untouched digits)
+  uint32_t done; // rot: number of stages already transformed (they sit in the low `done` bits of the position)
 };
 
 template <class F>
@@ -310,6 +312,8 @@ __global__ void __launch_bounds__(256, 2) k_ntt_tile(const uint32_t* __restrict_
   const uint32_t rev_shift = 64 - n_log;
   const uint64_t ntt_mask = (1ull << n_log) - 1;
   const uint64_t col0 = (uint64_t)blockIdx.x * C;
+  const uint32_t rsh = n_log - S;                   // rot: shift of the (top) digit being transformed
+  const uint64_t rmask = (1ull << rsh) - 1;         // rot: mask of everything below it
 
   F e[8];
   int a = (int)S;
@@ -333,7 +337,8 @@ __global__ void __launch_bounds__(256, 2) k_ntt_tile(const uint32_t* __restrict_
         const uint32_t m = eid[u] >> logC, c = eid[u] & (C - 1);
         const uint64_t colg = col0 + c;
         if (colg < total_cols) {
-          const uint64_t pos = ((colg >> lo) << (lo + S)) | ((uint64_t)m << lo) | (colg & ((1ull << lo) - 1)); // position incl. batch
+          const uint64_t pos = p.rot ? (((colg >> rsh) << n_log) | ((uint64_t)m << rsh) | (colg & rmask))                        // top digit
+                                     : (((colg >> lo) << (lo + S)) | ((uint64_t)m << lo) | (colg & ((1ull << lo) - 1)));         // position incl. batch
           const uint64_t pin = pos & ntt_mask;                                                                   // position inside its NTT
           uint64_t idx = pos;
           if (p.first && p.gather_in) idx = (pos & ~ntt_mask) | (__brevll(pin) >> rev_shift);
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(256, 2) k_ntt_tile(const uint32_t* __restrict_
         const int u = (g << q) & 7;
         const uint32_t m = eid[u] >> logC, c = eid[u] & (C - 1);
         mlo[g] = m & ((1u << a) - 1);
-        lowv[g] = (col0 + c) & ((1ull << lo) - 1);
+        lowv[g] = p.rot ? (((col0 + c) & rmask) >> p.done) : ((col0 + c) & ((1ull << lo) - 1));
       }
       if (q == 3) {
         const uint32_t m1[1] = {mlo[0]};
@@ -383,14 +388,26 @@ __global__ void __launch_bounds__(256, 2) k_ntt_tile(const uint32_t* __restrict_
         const uint32_t m = eid[u] >> logC, c = eid[u] & (C - 1);
         const uint64_t colg = col0 + c;
         if (colg >= total_cols) continue;
-        const uint64_t pos = ((colg >> lo) << (lo + S)) | ((uint64_t)m << lo) | (colg & ((1ull << lo) - 1));
-        const uint64_t pin = pos & ntt_mask;
-        uint64_t idx = pos;
-        if (p.last) {
-          const uint64_t kidx = n_log ? (__brevll(pin) >> rev_shift) : 0; // logical output index held at this position
-          if (p.out_mul) e[u] = e[u] * load_fp<F>(p.out_mul + kidx * F::N);
-          else if (p.out_scale) e[u] = e[u] * load_fp<F>(p.out_scale);
-          if (p.scatter_out) idx = (pos & ~ntt_mask) | kidx;
+        uint64_t idx;
+        if (p.rot) {
+          const uint64_t lowfull = colg & rmask;
+          const uint64_t mrev = (uint64_t)(__brev(m) >> (32 - S));
+          idx = ((colg >> rsh) << n_log) | ((lowfull >> p.done) << (S + p.done)) | (mrev << p.done) | (lowfull & ((1ull << p.done) - 1));
+          if (p.last) { // all digits transformed: idx is the natural frequency index
+            const uint64_t kidx = idx & ntt_mask;
+            if (p.out_mul) e[u] = e[u] * load_fp<F>(p.out_mul + kidx * F::N);
+            else if (p.out_scale) e[u] = e[u] * load_fp<F>(p.out_scale);
+          }
+        } else {
+          const uint64_t pos = ((colg >> lo) << (lo + S)) | ((uint64_t)m << lo) | (colg & ((1ull << lo) - 1));
+          const uint64_t pin = pos & ntt_mask;
+          idx = pos;
+          if (p.last) {
+            const uint64_t kidx = n_log ? (__brevll(pin) >> rev_shift) : 0; // logical output index held at this position
+            if (p.out_mul) e[u] = e[u] * load_fp<F>(p.out_mul + kidx * F::N);
+            else if (p.out_scale) e[u] = e[u] * load_fp<F>(p.out_scale);
+            if (p.scatter_out) idx = (pos & ~ntt_mask) | kidx;
+          }
         }
         store_fp<F>(dst + idx * F::N, e[u]);
       }
@@ -582,14 +599,6 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
   int radices[32];
   const int npass = use_tiles ? plan_tile_passes(n_log, radices) : plan_passes(n_log, maxr, radices);
 
-  // working buffer: see the header comment of this file for the in-place rules
-  const bool need_tmp = scatter_out || (gather_in && din == dout) || (npass == 1 && din == dout && (gather_in || scatter_out));
-  uint32_t* work = (uint32_t*)dout;
-  if (need_tmp) {
-    if ((err = stmp.alloc(bytes, s))) return err;
-    work = stmp.as<uint32_t>();
-  }
-
   PassParams p;
   memset(&p, 0, sizeof(p));
   p.tw = d->twiddles;
@@ -602,9 +611,56 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
   p.columns = cfg->columns_batch ? 1 : 0;
   p.bstride = cfg->columns_batch ? 1 : (uint64_t)size;
   p.estride = cfg->columns_batch ? batch : 1;
-
   StageTimer prof;
   prof.begin(s);
+
+  if (use_tiles && scatter_out) {
+    // ---- autosort schedule (natural-order output without a scatter): every pass transforms the TOP remaining digit and
+    // writes it bit-reversed just above the digits transformed so far, so stores land in contiguous runs and the last pass
+    // emits natural order.  Passes are out of place: in -> tmpA -> tmpB -> ... -> out.
+    Scratch stmpB;
+    if (npass >= 2 || din == dout) {
+      if ((err = stmp.alloc(bytes, s))) return err;
+    }
+    if (npass >= 3) {
+      if ((err = stmpB.alloc(bytes, s))) return err;
+    }
+    const uint32_t* src = (const uint32_t*)din;
+    if (npass == 1 && din == dout) {
+      B200_CUDA_TRY(cudaMemcpyAsync(stmp.p, din, bytes, cudaMemcpyDeviceToDevice, s), B200_COPY_FAILED);
+      src = stmp.as<uint32_t>();
+    }
+    p.rot = 1;
+    p.scatter_out = 0;
+    int done = 0;
+    for (int i = 0; i < npass; i++) {
+      const int r = radices[i];
+      p.done = (uint32_t)done;
+      p.lo = (uint32_t)(n_log - r - done); // untransformed bits below the digit: what the twiddle exponents see
+      p.first = (i == 0);
+      p.last = (i == npass - 1);
+      p.in_mul = p.first ? in_mul : nullptr;
+      p.out_mul = p.last ? out_mul : nullptr;
+      p.out_scale = p.last ? out_scale : nullptr;
+      uint32_t* dstp = p.last ? (uint32_t*)dout : ((i % 2 == 0) ? stmp.as<uint32_t>() : stmpB.as<uint32_t>());
+      if ((err = launch_tile_pass<F>(src, dstp, p, r, s))) return err;
+      prof.mark("pass");
+      src = dstp;
+      done += r;
+    }
+    prof.finish("ntt");
+    return finish_out(output, dout, bytes, cfg->are_outputs_on_device, cfg->is_async, s);
+  }
+
+  // ---- in-place schedule (bit-reversed output, or the register-only passes) ------------------------------------------------
+  // working buffer: pass 1 reads `in`; middle passes run in place; a permuting last pass needs a source distinct from `out`.
+  const bool need_tmp = scatter_out || (gather_in && din == dout) || (npass == 1 && din == dout && (gather_in || scatter_out));
+  uint32_t* work = (uint32_t*)dout;
+  if (need_tmp) {
+    if ((err = stmp.alloc(bytes, s))) return err;
+    work = stmp.as<uint32_t>();
+  }
+
   const uint32_t* src = (const uint32_t*)din;
   int hi = n_log;
   for (int i = 0; i < npass; i++) {

@@ -207,3 +207,19 @@ def test_linearity_large():
     B = common.projective_to_affine_ints(b, 8, q)
     Cc = common.projective_to_affine_ints(c, 8, q)
     assert common.ec_add(A, B, q) == Cc
+
+
+def test_pipelined_host_path_matches_device_path():
+    """Host-pointer calls with >= 2^23 points take the chunked copy/compute pipeline (msm_pipelined); the result must be the
+    same group element as the device-resident single-pass path."""
+    C = ib.Curve.BN254_G1
+    n = 1 << 23
+    base = common.gen_g1_points("bn254", 1 << 10, 321)
+    P = np.tile(base, (n >> 10, 1))
+    rs = np.random.RandomState(9)
+    s = rs.randint(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+    s[:, 7] &= 0x0FFFFFFF
+    host = ib.msm(C, s, P, n)[0]                                  # host pointers -> pipelined
+    dev = ib.msm(C, ib.to_device(s), ib.to_device(P), n)[0]       # device pointers -> single pass
+    q = utils.field_params("bn254_fq")["p"]
+    assert common.projective_to_affine_ints(host, 8, q) == common.projective_to_affine_ints(dev, 8, q)
