@@ -29,9 +29,25 @@ struct Scratch {
   Scratch() = default;
   Scratch(const Scratch&) = delete;
   Scratch& operator=(const Scratch&) = delete;
+  // Keep freed scratch in the device's default pool (MSM / NTT temporaries are re-used call after call); without this the
+  // pool hands memory back to the driver at every synchronisation and each call pays the allocation again.
+  static void ensure_pool_configured()
+  {
+    static thread_local unsigned long long configured_mask = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    if (configured_mask & (1ull << dev)) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thresh = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    configured_mask |= (1ull << dev);
+  }
   int alloc(size_t bytes, cudaStream_t stream)
   {
     release();
+    ensure_pool_configured();
     s = stream;
     if (bytes == 0) bytes = 16;
     cudaError_t e = cudaMallocAsync(&p, bytes, stream);
