@@ -401,6 +401,41 @@ def _unary(fn_name, field_or_curve, a, n_out_elems, limbs, config, output, *extr
     return fn, ap, op, c, output
 
 
+def vector_inv(field, a, size, config=None, output=None):
+    cfg = config or VecOpsConfig()
+    fn, ap, op, c, output = _unary("b200_vector_inv", field, a, size * cfg.batch_size, field_limbs(field), cfg, output)
+    check(fn(int(field), ap, int(size), C.byref(c), op), "vector_inv")
+    return output
+
+
+def vector_div(field, a, b, size, config=None, output=None):
+    cfg = copy.copy(config) if config else VecOpsConfig()
+    ap, a_dev, _ka = _ptr(a)
+    bp, b_dev, _kb = _ptr(b)
+    cfg.is_a_on_device, cfg.is_b_on_device = a_dev, b_dev
+    if output is None:
+        output = _out_like(field, size * cfg.batch_size, cfg.is_result_on_device)
+    op, o_dev, _ko = _ptr(output)
+    cfg.is_result_on_device = o_dev
+    c = cfg._c()
+    check(lib.b200_vector_div(int(field), ap, bp, int(size), C.byref(c), op), "vector_div")
+    return output
+
+
+def vector_sum(field, a, size, config=None, output=None):
+    cfg = config or VecOpsConfig()
+    fn, ap, op, c, output = _unary("b200_vector_sum", field, a, cfg.batch_size, field_limbs(field), cfg, output)
+    check(fn(int(field), ap, int(size), C.byref(c), op), "vector_sum")
+    return output
+
+
+def vector_product(field, a, size, config=None, output=None):
+    cfg = config or VecOpsConfig()
+    fn, ap, op, c, output = _unary("b200_vector_product", field, a, cfg.batch_size, field_limbs(field), cfg, output)
+    check(fn(int(field), ap, int(size), C.byref(c), op), "vector_product")
+    return output
+
+
 def convert_montgomery(field, a, size, is_into, config=None, output=None):
     cfg = config or VecOpsConfig()
     fn, ap, op, c, output = _unary("b200_convert_montgomery", field, a, size * cfg.batch_size, field_limbs(field), cfg, output)

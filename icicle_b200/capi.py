@@ -85,6 +85,10 @@ SYMBOLS = {
     "b200_ntt": (_i, [_i, _vp, _i, _i, C.POINTER(NttConfigC), _vp]),
     "b200_vec_ops_default_config": (None, [C.POINTER(VecOpsConfigC)]),
     "b200_vec_op": (_i, [_i, _i, _vp, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
+    "b200_vector_inv": (_i, [_i, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
+    "b200_vector_div": (_i, [_i, _vp, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
+    "b200_vector_sum": (_i, [_i, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
+    "b200_vector_product": (_i, [_i, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
     "b200_convert_montgomery": (_i, [_i, _vp, _u64, _i, C.POINTER(VecOpsConfigC), _vp]),
     "b200_bit_reverse": (_i, [_i, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
     "b200_matrix_transpose": (_i, [_i, _vp, _u32, _u32, C.POINTER(VecOpsConfigC), _vp]),

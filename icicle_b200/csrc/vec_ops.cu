@@ -7,6 +7,7 @@
 // fields), grid sized as a multiple of the SM count with a grid-stride loop.  Algorithmic bytes: 3*|S| per element for
 // the binary ops, 2*|S| for the unary ones.
 #include "common.cuh"
+#include <algorithm>
 #include <cstring>
 
 using namespace b200;
@@ -181,6 +182,167 @@ int convert_mont_impl(const void* in, uint64_t n, int is_into, const b200_vec_op
   return finish_out(out, dout, bytes, cfg->is_result_on_device, cfg->is_async, s);
 }
 
+
+// a^(p-2) in the Montgomery domain (Fermat); 0 -> 0, which is the reference's inverse(0) (modular_arithmetic.h:621-623)
+template <class F>
+__device__ F fermat_inv_mont(const F& a_m)
+{
+  uint32_t e[F::N];
+#pragma unroll
+  for (int i = 0; i < F::N; i++) e[i] = F::P::p(i);
+  uint32_t borrow = 2;
+  for (int i = 0; i < F::N && borrow; i++) {
+    uint32_t before = e[i];
+    e[i] = before - borrow;
+    borrow = (before < borrow) ? 1u : 0u;
+  }
+  F r = F::one();
+  for (int i = F::N * 32 - 1; i >= 0; i--) {
+    r = r * r;
+    if ((e[i / 32] >> (i % 32)) & 1) r = r * a_m;
+  }
+  return r;
+}
+
+// out[i] = a[i]^-1 (DIV: num[i] * a[i]^-1), standard form in and out.  Each thread inverts K elements with one field
+// inversion (Montgomery's trick); zeros are passed through as zeros like the reference's inverse().
+template <class F, bool DIV, int K>
+__global__ void __launch_bounds__(128) k_vec_inv(const uint32_t* __restrict__ num, const uint32_t* __restrict__ a, uint32_t* out, uint64_t n)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t i0 = t * K;
+  if (i0 >= n) return;
+  F x[K], pre[K];
+  bool nz[K];
+  F acc = F::one();
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    if (i0 + k < n) {
+      x[k] = load_fp<F>(a + (i0 + k) * F::N).to_mont();
+      nz[k] = !x[k].is_zero();
+    } else {
+      nz[k] = false;
+    }
+    pre[k] = acc;                 // product of the non-zero elements before k
+    if (nz[k]) acc = acc * x[k];
+  }
+  F inv = fermat_inv_mont(acc);   // (prod)^-1 in Montgomery form
+#pragma unroll
+  for (int k = K - 1; k >= 0; k--) {
+    if (i0 + k >= n) continue;
+    F r = F::zero();
+    if (nz[k]) {
+      r = inv * pre[k];           // x[k]^-1 * R
+      inv = inv * x[k];
+    }
+    // out = (x^-1 R) -> standard form; for DIV multiply the standard-form numerator by the Montgomery-form inverse
+    if (DIV) r = load_fp<F>(num + (i0 + k) * F::N) * r;
+    else r = r.from_mont();
+    store_fp<F>(out + (i0 + k) * F::N, r);
+  }
+}
+
+// per-batch reduction (sum or product), two levels: block partials, then one block per batch element
+template <class F, bool PRODUCT>
+__global__ void __launch_bounds__(256)
+k_reduce(const uint32_t* __restrict__ a, uint64_t size, uint32_t batch, bool columns, uint32_t blocks_per_batch, uint32_t* __restrict__ partial)
+{
+  __shared__ uint32_t sm[256 * F::N];
+  const uint32_t b = blockIdx.x / blocks_per_batch, blk = blockIdx.x % blocks_per_batch;
+  F acc = PRODUCT ? F::one() : F::zero();
+  for (uint64_t i = (uint64_t)blk * 256 + threadIdx.x; i < size; i += (uint64_t)blocks_per_batch * 256) {
+    const uint64_t idx = columns ? (i * batch + b) : ((uint64_t)b * size + i);
+    F x = load_fp<F>(a + idx * F::N);
+    acc = PRODUCT ? acc * x.to_mont() : acc + x;
+  }
+#pragma unroll
+  for (int l = 0; l < F::N; l++) sm[l * 256 + threadIdx.x] = acc.v[l];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      F x, y;
+#pragma unroll
+      for (int l = 0; l < F::N; l++) { x.v[l] = sm[l * 256 + threadIdx.x]; y.v[l] = sm[l * 256 + threadIdx.x + s]; }
+      x = PRODUCT ? x * y : x + y;
+#pragma unroll
+      for (int l = 0; l < F::N; l++) sm[l * 256 + threadIdx.x] = x.v[l];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    F r;
+#pragma unroll
+    for (int l = 0; l < F::N; l++) r.v[l] = sm[l * 256];
+    store_fp<F>(partial + (uint64_t)blockIdx.x * F::N, r); // product partials stay in Montgomery form
+  }
+}
+template <class F, bool PRODUCT>
+__global__ void k_reduce_final(const uint32_t* __restrict__ partial, uint32_t blocks_per_batch, uint32_t batch, uint32_t* __restrict__ out)
+{
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  F acc = PRODUCT ? F::one() : F::zero();
+  for (uint32_t k = 0; k < blocks_per_batch; k++) {
+    F x = load_fp<F>(partial + ((uint64_t)b * blocks_per_batch + k) * F::N);
+    acc = PRODUCT ? acc * x : acc + x;
+  }
+  if (PRODUCT) acc = acc.from_mont();
+  store_fp<F>(out + (uint64_t)b * F::N, acc);
+}
+
+template <class F>
+int inv_div_impl(bool div, const void* num, const void* a, uint64_t size, const b200_vec_ops_config* cfg, void* out)
+{
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  const uint64_t n = size * (cfg->batch_size > 0 ? cfg->batch_size : 1);
+  if (n == 0) return B200_SUCCESS;
+  const size_t bytes = n * F::BYTES;
+  Scratch sn, sa, so;
+  const void *dn = nullptr, *da;
+  void* dout;
+  int err;
+  if (div && (err = stage_in(dn, num, bytes, cfg->is_a_on_device, s, sn))) return err;
+  if ((err = stage_in(da, a, bytes, div ? cfg->is_b_on_device : cfg->is_a_on_device, s, sa))) return err;
+  if ((err = stage_out(dout, out, bytes, cfg->is_result_on_device, s, so))) return err;
+  constexpr int K = 8;
+  const uint64_t threads = (n + K - 1) / K;
+  const unsigned g = (unsigned)((threads + 127) / 128);
+  if (div) {
+    k_vec_inv<F, true, K><<<g, 128, 0, s>>>((const uint32_t*)dn, (const uint32_t*)da, (uint32_t*)dout, n); B200_LAUNCHED(1);
+  } else {
+    k_vec_inv<F, false, K><<<g, 128, 0, s>>>(nullptr, (const uint32_t*)da, (uint32_t*)dout, n); B200_LAUNCHED(1);
+  }
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  return finish_out(out, dout, bytes, cfg->is_result_on_device, cfg->is_async, s);
+}
+
+template <class F>
+int reduce_impl(bool product, const void* a, uint64_t size, const b200_vec_ops_config* cfg, void* out)
+{
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  const uint32_t batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
+  if (size == 0) return B200_INVALID_ARGUMENT;
+  const size_t bytes = size * batch * F::BYTES;
+  Scratch sa, so, sp;
+  const void* da;
+  void* dout;
+  int err;
+  if ((err = stage_in(da, a, bytes, cfg->is_a_on_device, s, sa))) return err;
+  if ((err = stage_out(dout, out, (size_t)batch * F::BYTES, cfg->is_result_on_device, s, so))) return err;
+  uint32_t bpb = (uint32_t)std::min<uint64_t>((size + 2047) / 2048, std::max<uint32_t>(1, (uint32_t)num_sms() * 8 / batch));
+  if (bpb == 0) bpb = 1;
+  if ((err = sp.alloc((size_t)batch * bpb * F::BYTES, s))) return err;
+  if (product) {
+    k_reduce<F, true><<<batch * bpb, 256, 0, s>>>((const uint32_t*)da, size, batch, cfg->columns_batch, bpb, sp.as<uint32_t>()); B200_LAUNCHED(1);
+    k_reduce_final<F, true><<<(batch + 63) / 64, 64, 0, s>>>(sp.as<uint32_t>(), bpb, batch, (uint32_t*)dout); B200_LAUNCHED(1);
+  } else {
+    k_reduce<F, false><<<batch * bpb, 256, 0, s>>>((const uint32_t*)da, size, batch, cfg->columns_batch, bpb, sp.as<uint32_t>()); B200_LAUNCHED(1);
+    k_reduce_final<F, false><<<(batch + 63) / 64, 64, 0, s>>>(sp.as<uint32_t>(), bpb, batch, (uint32_t*)dout); B200_LAUNCHED(1);
+  }
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  return finish_out(out, dout, (size_t)batch * F::BYTES, cfg->is_result_on_device, cfg->is_async, s);
+}
+
 int curve_base_field(int curve, int* coords_per_point_factor)
 {
   *coords_per_point_factor = 1;
@@ -212,6 +374,31 @@ int b200_vec_op(int field, int op, const void* a, const void* b, uint64_t size, 
 {
   if (!cfg || !a || !b) return B200_INVALID_POINTER;
   B200_DISPATCH_FIELD(field, return vec_op_impl<F>(op, a, b, size, cfg, out));
+  return B200_INVALID_ARGUMENT;
+}
+
+int b200_vector_inv(int field, const void* a, uint64_t size, const b200_vec_ops_config* cfg, void* out)
+{
+  if (!cfg || !a || !out) return B200_INVALID_POINTER;
+  B200_DISPATCH_FIELD(field, return inv_div_impl<F>(false, nullptr, a, size, cfg, out));
+  return B200_INVALID_ARGUMENT;
+}
+int b200_vector_div(int field, const void* a, const void* b, uint64_t size, const b200_vec_ops_config* cfg, void* out)
+{
+  if (!cfg || !a || !b || !out) return B200_INVALID_POINTER;
+  B200_DISPATCH_FIELD(field, return inv_div_impl<F>(true, a, b, size, cfg, out));
+  return B200_INVALID_ARGUMENT;
+}
+int b200_vector_sum(int field, const void* a, uint64_t size, const b200_vec_ops_config* cfg, void* out)
+{
+  if (!cfg || !a || !out) return B200_INVALID_POINTER;
+  B200_DISPATCH_FIELD(field, return reduce_impl<F>(false, a, size, cfg, out));
+  return B200_INVALID_ARGUMENT;
+}
+int b200_vector_product(int field, const void* a, uint64_t size, const b200_vec_ops_config* cfg, void* out)
+{
+  if (!cfg || !a || !out) return B200_INVALID_POINTER;
+  B200_DISPATCH_FIELD(field, return reduce_impl<F>(true, a, size, cfg, out));
   return B200_INVALID_ARGUMENT;
 }
 

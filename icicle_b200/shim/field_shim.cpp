@@ -2,7 +2,7 @@
 // Hooks used (icicle/include/icicle/backend/ntt_backend.h:23,57,72,85; vec_ops_backend.h:87-226):
 //   REGISTER_NTT_BACKEND, REGISTER_NTT_INIT_DOMAIN_BACKEND, REGISTER_NTT_RELEASE_DOMAIN_BACKEND,
 //   REGISTER_NTT_GET_ROU_FROM_DOMAIN_BACKEND, REGISTER_VECTOR_{ADD,ACCUMULATE,SUB,MUL}_BACKEND,
-//   REGISTER_SCALAR_{MUL,ADD,SUB}_VEC_BACKEND, REGISTER_CONVERT_MONTGOMERY_BACKEND, REGISTER_BIT_REVERSE_BACKEND,
+//   REGISTER_SCALAR_{MUL,ADD,SUB}_VEC_BACKEND, REGISTER_VECTOR_{INV,DIV,SUM,PRODUCT}_BACKEND, REGISTER_CONVERT_MONTGOMERY_BACKEND, REGISTER_BIT_REVERSE_BACKEND,
 //   REGISTER_SLICE_BACKEND, REGISTER_MATRIX_TRANSPOSE_BACKEND.
 // Each lambda translates the reference config (ntt.h:52-64, vec_ops.h:19-44) to the C structs and forwards.
 #include "shim_common.h"
@@ -48,6 +48,26 @@ namespace {
   {
     b200_vec_ops_config c = to_c(config);
     return to_err(b200_vec_op(FIELD, B200_VEC_ACCUMULATE, a, b, size, &c, a));
+  }
+  eIcicleError vec_inv(const Device&, const scalar_t* a, uint64_t size, const VecOpsConfig& config, scalar_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_vector_inv(FIELD, a, size, &c, out));
+  }
+  eIcicleError vec_div(const Device&, const scalar_t* a, const scalar_t* b, uint64_t size, const VecOpsConfig& config, scalar_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_vector_div(FIELD, a, b, size, &c, out));
+  }
+  eIcicleError vec_sum(const Device&, const scalar_t* a, uint64_t size, const VecOpsConfig& config, scalar_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_vector_sum(FIELD, a, size, &c, out));
+  }
+  eIcicleError vec_product(const Device&, const scalar_t* a, uint64_t size, const VecOpsConfig& config, scalar_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_vector_product(FIELD, a, size, &c, out));
   }
   eIcicleError convert_mont(const Device&, const scalar_t* in, uint64_t size, bool is_into, const VecOpsConfig& config, scalar_t* out)
   {
@@ -108,6 +128,10 @@ REGISTER_VECTOR_ACCUMULATE_BACKEND(B200_DEVICE_TYPE, accumulate);
 REGISTER_SCALAR_ADD_VEC_BACKEND(B200_DEVICE_TYPE, vec2<B200_SCALAR_ADD_VEC>);
 REGISTER_SCALAR_SUB_VEC_BACKEND(B200_DEVICE_TYPE, vec2<B200_SCALAR_SUB_VEC>);
 REGISTER_SCALAR_MUL_VEC_BACKEND(B200_DEVICE_TYPE, vec2<B200_SCALAR_MUL_VEC>);
+REGISTER_VECTOR_INV_BACKEND(B200_DEVICE_TYPE, vec_inv);
+REGISTER_VECTOR_DIV_BACKEND(B200_DEVICE_TYPE, vec_div);
+REGISTER_VECTOR_SUM_BACKEND(B200_DEVICE_TYPE, vec_sum);
+REGISTER_VECTOR_PRODUCT_BACKEND(B200_DEVICE_TYPE, vec_product);
 REGISTER_CONVERT_MONTGOMERY_BACKEND(B200_DEVICE_TYPE, convert_mont);
 REGISTER_BIT_REVERSE_BACKEND(B200_DEVICE_TYPE, bit_rev);
 REGISTER_SLICE_BACKEND(B200_DEVICE_TYPE, slice_op);

@@ -199,6 +199,13 @@ typedef enum {
 B200_API void b200_vec_ops_default_config(b200_vec_ops_config* cfg);
 /* element-wise op over size*batch_size elements (scalar_* ops: `a` holds one scalar per batch, cpu_vec_ops.cpp:325-341) */
 B200_API int b200_vec_op(int field, int op, const void* a, const void* b, uint64_t size, const b200_vec_ops_config* cfg, void* out);
+/* vector_inv / vector_div: out = a^-1, out = a / b element-wise; inverse(0) = 0 like the reference (modular_arithmetic.h:621-623)
+ * REGISTER_VECTOR_INV_BACKEND / REGISTER_VECTOR_DIV_BACKEND (vec_ops_backend.h:107,136); cpu_vec_ops.cpp:386-403 */
+B200_API int b200_vector_inv(int field, const void* a, uint64_t size, const b200_vec_ops_config* cfg, void* out);
+B200_API int b200_vector_div(int field, const void* a, const void* b, uint64_t size, const b200_vec_ops_config* cfg, void* out);
+/* vector_sum / vector_product: one output element per batch (VectorReduceOpImpl, vec_ops_backend.h:22-23,156,166; cpu_vec_ops.cpp:428-490) */
+B200_API int b200_vector_sum(int field, const void* a, uint64_t size, const b200_vec_ops_config* cfg, void* out);
+B200_API int b200_vector_product(int field, const void* a, uint64_t size, const b200_vec_ops_config* cfg, void* out);
 /* convert_montgomery (vec_ops_backend.h ConvertMontgomery; cpu_vec_ops.cpp) */
 B200_API int b200_convert_montgomery(int field, const void* in, uint64_t size, int is_into, const b200_vec_ops_config* cfg, void* out);
 /* bit_reverse (cpu_vec_ops.cpp:535-575): out[i] = in[bitrev(i)], size must be a power of two */

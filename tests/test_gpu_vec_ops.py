@@ -38,6 +38,33 @@ def test_vector_ops_vs_python(field, name):
     assert utils.from_limbs(ib.convert_montgomery(field, A, n, False)) == [x * pow(R, -1, p) % p for x in a]
 
 
+@pytest.mark.parametrize("field,name", FIELDS[:1] + FIELDS[3:4] + FIELDS[8:9])
+def test_inv_div_sum_product(field, name):
+    """vector_inv / vector_div / vector_sum / vector_product (cpu_vec_ops.cpp:386-403,428-490); inverse(0) = 0."""
+    fp = utils.field_params(name)
+    p, L = fp["p"], fp["limbs"]
+    n = 1000 + 3
+    a = common.rand_field_elems(name, n, 21, as_ints=True)
+    b = common.rand_field_elems(name, n, 22, as_ints=True)
+    a[5], a[6], b[7] = 0, 1, 0
+    A, B = utils.to_limbs(a, L), utils.to_limbs(b, L)
+    inv = lambda x: pow(x, -1, p) if x else 0
+    assert utils.from_limbs(ib.vector_inv(field, A, n)) == [inv(x) for x in a]
+    assert utils.from_limbs(ib.vector_div(field, A, B, n)) == [x * inv(y) % p for x, y in zip(a, b)]
+    size, batch = 333, 3
+    for columns in (False, True):
+        cfg = ib.VecOpsConfig(batch_size=batch, columns_batch=columns)
+        rows = [[a[(i * batch + bb) if columns else (bb * size + i)] for i in range(size)] for bb in range(batch)]
+        assert utils.from_limbs(ib.vector_sum(field, A[: size * batch], size, cfg)) == [sum(r) % p for r in rows]
+        prods = []
+        for r in rows:
+            acc = 1
+            for x in r:
+                acc = acc * x % p
+            prods.append(acc)
+        assert utils.from_limbs(ib.vector_product(field, A[: size * batch], size, cfg)) == prods
+
+
 @pytest.mark.parametrize("field,name", FIELDS[:1] + FIELDS[8:9])
 @pytest.mark.parametrize("columns", [False, True])
 def test_scalar_vec_ops_batch(field, name, columns):
