@@ -234,44 +234,58 @@ __global__ void __launch_bounds__(128) k_ntt_pass(const uint32_t* __restrict__ s
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// v2 pass: shared-memory tile.  One CTA (256 threads) transforms a tile of 2048 elements = C columns x 2^S strided rows
-// (C = 2^(11-S)), S = 5..9 DIF stages per pass, as rounds of <= 3 stages kept in registers (8 elements per thread) with
-// the tile exchanged through shared memory between rounds.  A 2^24 transform is 3 HBM round trips (8+8+8 stages).
+// v2 pass: shared-memory tile.  One CTA of 2^LOGT threads transforms a tile of 2^(LOGT+LOGE) elements = C columns x 2^S
+// strided rows, S DIF stages per pass, as rounds of <= LOGE stages kept in registers (2^LOGE elements per thread) with the
+// tile exchanged through shared memory between rounds.  256-bit fields use LOGE = 3, LOGT = 8 (2048-element tile, 8
+// elements = 64 registers per thread; a 2^24 transform is 3 HBM round trips of 8+8+8 stages); the 31-bit fields
+// (BabyBear / KoalaBear, one register per element, HBM-bound) use LOGE = 5, LOGT = 9 (16384-element tile, radix-32
+// rounds, 128-byte rows at S = 9).
 // Shared memory holds the tile limb-major ([limb][element], padded by one word per 32 elements): a warp reads one limb
 // of 32 consecutive elements per LDS, so the round-to-round exchange is bank-conflict-free in the long-stride rounds and
-// at most 4-way conflicted in the short last round -- far below the IMAD.WIDE time of the 12 Montgomery products a
-// thread does per round.  Twiddles come from the Montgomery-form domain table (7 loads per 8-element radix-8 group).
+// at most 4-way conflicted in the short last round -- far below the IMAD.WIDE time of the Montgomery products a thread
+// does per round.  Twiddles come from the Montgomery-form domain table (2^q - 1 loads per 2^q-element group).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int TILE_LOG = 11;
-constexpr int TILE = 1 << TILE_LOG;
-constexpr int TILE_PAD = TILE + TILE / 32;
+template <int TILE_LOG>
+struct TileGeom {
+  static constexpr int TILE = 1 << TILE_LOG;
+  static constexpr int PAD = TILE + TILE / 32;
+};
 
 __device__ __forceinline__ uint32_t tile_slot(uint32_t e) { return e + (e >> 5); }
 
-template <class F>
+template <class F, int PAD>
 __device__ __forceinline__ F tile_load(const uint32_t* sm, uint32_t e)
 {
   F r;
   const uint32_t s = tile_slot(e);
 #pragma unroll
-  for (int i = 0; i < F::N; i++) r.v[i] = sm[i * TILE_PAD + s];
+  for (int i = 0; i < F::N; i++) r.v[i] = sm[i * PAD + s];
   return r;
 }
-template <class F>
+template <class F, int PAD>
 __device__ __forceinline__ void tile_store(uint32_t* sm, uint32_t e, const F& a)
 {
   const uint32_t s = tile_slot(e);
 #pragma unroll
-  for (int i = 0; i < F::N; i++) sm[i * TILE_PAD + s] = a.v[i];
+  for (int i = 0; i < F::N; i++) sm[i * PAD + s] = a.v[i];
 }
 
-// Q DIF stages (local stages [a, a+Q)) on the 8 register-resident elements of this thread: 2^(3-Q) groups of 2^Q.
-// jbase[grp] = (m mod 2^a) of the group's elements (bits of m below the round), low/lo/dom as in the v1 pass.
-template <class F, int Q>
-__device__ __forceinline__ void tile_round(F (&e)[8], const PassParams& p, uint32_t a, const uint32_t (&mlo)[8 >> Q], const uint64_t (&low)[8 >> Q])
+// Q DIF stages (local stages [a, a+Q)) on the E = 2^LOGE register-resident elements of this thread: 2^(LOGE-Q) groups of
+// 2^Q.  mlo[g] = (m mod 2^a) of group g's elements, low[g] = the untransformed index below the digit (twiddle argument).
+template <class F, int LOGE, int Q>
+__device__ __forceinline__ void tile_round(F (&e)[1 << LOGE], const PassParams& p, uint32_t a, const uint32_t* eid, uint32_t logC, uint64_t col0,
+                                           uint64_t rmask)
 {
-  constexpr int G = 8 >> Q;
+  constexpr int G = (1 << LOGE) >> Q;
   const uint64_t dom_mask = (1ull << p.dom_log) - 1;
+  uint32_t mlo[G];
+  uint64_t low[G];
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    const uint32_t m = eid[g << Q] >> logC, c = eid[g << Q] & ((1u << logC) - 1);
+    mlo[g] = m & ((1u << a) - 1);
+    low[g] = p.rot ? (((col0 + c) & rmask) >> p.done) : ((col0 + c) & ((1ull << p.lo) - 1));
+  }
 #pragma unroll
   for (int i = Q - 1; i >= 0; --i) {
     const uint32_t s = p.lo + a + i; // global stage
@@ -302,9 +316,28 @@ __device__ __forceinline__ void tile_round(F (&e)[8], const PassParams& p, uint3
   }
 }
 
-template <class F>
-__global__ void __launch_bounds__(256, 2) k_ntt_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassParams p, uint32_t S, uint64_t total_cols)
+template <class F, int LOGE, int Q>
+struct RoundDispatch {
+  static __device__ __forceinline__ void run(int q, F (&e)[1 << LOGE], const PassParams& p, uint32_t a, const uint32_t* eid, uint32_t logC,
+                                             uint64_t col0, uint64_t rmask)
+  {
+    if (q == Q) tile_round<F, LOGE, Q>(e, p, a, eid, logC, col0, rmask);
+    else RoundDispatch<F, LOGE, Q - 1>::run(q, e, p, a, eid, logC, col0, rmask);
+  }
+};
+template <class F, int LOGE>
+struct RoundDispatch<F, LOGE, 0> {
+  static __device__ __forceinline__ void run(int, F (&)[1 << LOGE], const PassParams&, uint32_t, const uint32_t*, uint32_t, uint64_t, uint64_t) {}
+};
+
+template <class F, int LOGE, int LOGT>
+__global__ void __launch_bounds__(1 << LOGT, (LOGT >= 9 ? 1 : 2))
+k_ntt_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassParams p, uint32_t S, uint64_t total_cols)
 {
+  constexpr int E = 1 << LOGE;
+  constexpr int NT = 1 << LOGT;
+  constexpr int TILE_LOG = LOGE + LOGT;
+  constexpr int PAD = TileGeom<TILE_LOG>::PAD;
   extern __shared__ uint32_t sm[];
   const uint32_t T = threadIdx.x;
   const uint32_t logC = TILE_LOG - S, C = 1u << logC;
@@ -312,34 +345,34 @@ __global__ void __launch_bounds__(256, 2) k_ntt_tile(const uint32_t* __restrict_
   const uint32_t rev_shift = 64 - n_log;
   const uint64_t ntt_mask = (1ull << n_log) - 1;
   const uint64_t col0 = (uint64_t)blockIdx.x * C;
-  const uint32_t rsh = n_log - S;                   // rot: shift of the (top) digit being transformed
-  const uint64_t rmask = (1ull << rsh) - 1;         // rot: mask of everything below it
+  const uint32_t rsh = n_log - S;           // rot: shift of the (top) digit being transformed
+  const uint64_t rmask = (1ull << rsh) - 1; // rot: mask of everything below it
 
-  F e[8];
+  F e[E];
   int a = (int)S;
   bool first_round = true;
   while (a > 0) {
-    const int q = (a >= 3) ? 3 : a;
+    const int q = (a >= LOGE) ? LOGE : a;
     a -= q;
     const bool last_round = (a == 0);
     const uint32_t P = (uint32_t)a + logC;
-    uint32_t eid[8];
+    uint32_t eid[E];
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
+    for (int u = 0; u < E; u++) {
       const uint32_t k = u & ((1u << q) - 1), grp = u >> q;
-      const uint32_t rest = T + 256u * grp;
+      const uint32_t rest = T + (uint32_t)NT * grp;
       eid[u] = ((rest >> P) << (P + q)) | (k << P) | (rest & ((1u << P) - 1));
     }
     // ---- load ----
     if (first_round) {
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
+      for (int u = 0; u < E; u++) {
         const uint32_t m = eid[u] >> logC, c = eid[u] & (C - 1);
         const uint64_t colg = col0 + c;
         if (colg < total_cols) {
-          const uint64_t pos = p.rot ? (((colg >> rsh) << n_log) | ((uint64_t)m << rsh) | (colg & rmask))                        // top digit
-                                     : (((colg >> lo) << (lo + S)) | ((uint64_t)m << lo) | (colg & ((1ull << lo) - 1)));         // position incl. batch
-          const uint64_t pin = pos & ntt_mask;                                                                   // position inside its NTT
+          const uint64_t pos = p.rot ? (((colg >> rsh) << n_log) | ((uint64_t)m << rsh) | (colg & rmask))                // top digit
+                                     : (((colg >> lo) << (lo + S)) | ((uint64_t)m << lo) | (colg & ((1ull << lo) - 1))); // position incl. batch
+          const uint64_t pin = pos & ntt_mask;                                                                          // position inside its NTT
           uint64_t idx = pos;
           if (p.first && p.gather_in) idx = (pos & ~ntt_mask) | (__brevll(pin) >> rev_shift);
           e[u] = load_fp<F>(src + idx * F::N);
@@ -351,40 +384,15 @@ __global__ void __launch_bounds__(256, 2) k_ntt_tile(const uint32_t* __restrict_
     } else {
       __syncthreads(); // previous round's stores are visible
 #pragma unroll
-      for (int u = 0; u < 8; u++) e[u] = tile_load<F>(sm, eid[u]);
+      for (int u = 0; u < E; u++) e[u] = tile_load<F, PAD>(sm, eid[u]);
       __syncthreads(); // everyone has read before anyone overwrites
     }
     // ---- butterflies ----
-    {
-      // per group: m_lo (bits of m below the round) and the column's low index
-      uint32_t mlo[8];
-      uint64_t lowv[8];
-#pragma unroll
-      for (int g = 0; g < 8; g++) {
-        // group g of this round starts at element u = g << q (only the first 8>>q entries are used)
-        const int u = (g << q) & 7;
-        const uint32_t m = eid[u] >> logC, c = eid[u] & (C - 1);
-        mlo[g] = m & ((1u << a) - 1);
-        lowv[g] = p.rot ? (((col0 + c) & rmask) >> p.done) : ((col0 + c) & ((1ull << lo) - 1));
-      }
-      if (q == 3) {
-        const uint32_t m1[1] = {mlo[0]};
-        const uint64_t l1[1] = {lowv[0]};
-        tile_round<F, 3>(e, p, (uint32_t)a, m1, l1);
-      } else if (q == 2) {
-        const uint32_t m2[2] = {mlo[0], mlo[1]};
-        const uint64_t l2[2] = {lowv[0], lowv[1]};
-        tile_round<F, 2>(e, p, (uint32_t)a, m2, l2);
-      } else {
-        const uint32_t m4[4] = {mlo[0], mlo[1], mlo[2], mlo[3]};
-        const uint64_t l4[4] = {lowv[0], lowv[1], lowv[2], lowv[3]};
-        tile_round<F, 1>(e, p, (uint32_t)a, m4, l4);
-      }
-    }
+    RoundDispatch<F, LOGE, LOGE>::run(q, e, p, (uint32_t)a, eid, logC, col0, rmask);
     // ---- store ----
     if (last_round) {
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
+      for (int u = 0; u < E; u++) {
         const uint32_t m = eid[u] >> logC, c = eid[u] & (C - 1);
         const uint64_t colg = col0 + c;
         if (colg >= total_cols) continue;
@@ -413,30 +421,40 @@ __global__ void __launch_bounds__(256, 2) k_ntt_tile(const uint32_t* __restrict_
       }
     } else {
 #pragma unroll
-      for (int u = 0; u < 8; u++) tile_store<F>(sm, eid[u], e[u]);
+      for (int u = 0; u < E; u++) tile_store<F, PAD>(sm, eid[u], e[u]);
     }
     first_round = false;
   }
 }
 
+// tile geometry per field width: elements per thread (2^LOGE) and threads per CTA (2^LOGT)
+template <class F>
+struct TileCfg {
+  static constexpr int LOGE = (F::N == 1) ? 5 : (F::N >= 12 ? 2 : 3);
+  static constexpr int LOGT = (F::N == 1) ? 9 : 8;
+  static constexpr int TILE_LOG = LOGE + LOGT;
+  static constexpr int MAX_S = (F::N == 1) ? 10 : 9; // stages per pass
+};
+
 template <class F>
 int launch_tile_pass(const uint32_t* src, uint32_t* dst, const PassParams& p, int S, cudaStream_t s)
 {
+  constexpr int LOGE = TileCfg<F>::LOGE, LOGT = TileCfg<F>::LOGT, TILE_LOG = TileCfg<F>::TILE_LOG;
   const uint64_t total = ((uint64_t)1 << p.n_log) * p.batch;
   const uint64_t total_cols = total >> S;
   const uint32_t C = 1u << (TILE_LOG - S);
   const uint64_t blocks = (total_cols + C - 1) / C;
-  const size_t smem = (size_t)TILE_PAD * F::N * 4;
-  B200_CUDA_TRY(cudaFuncSetAttribute(k_ntt_tile<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), B200_UNKNOWN_ERROR);
-  k_ntt_tile<F><<<(unsigned)blocks, 256, smem, s>>>(src, dst, p, (uint32_t)S, total_cols); B200_LAUNCHED(1);
+  const size_t smem = (size_t)TileGeom<TILE_LOG>::PAD * F::N * 4;
+  B200_CUDA_TRY(cudaFuncSetAttribute(k_ntt_tile<F, LOGE, LOGT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), B200_UNKNOWN_ERROR);
+  k_ntt_tile<F, LOGE, LOGT><<<(unsigned)blocks, 1 << LOGT, smem, s>>>(src, dst, p, (uint32_t)S, total_cols); B200_LAUNCHED(1);
   B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
   return B200_SUCCESS;
 }
 
-// split n_log stages into tile passes of 5..9 stages (as few passes as possible, sizes as even as possible)
-int plan_tile_passes(int n_log, int* S)
+// split n_log stages into tile passes of at most max_s stages (as few passes as possible, sizes as even as possible)
+int plan_tile_passes(int n_log, int max_s, int* S)
 {
-  int k = (n_log + 8) / 9;
+  int k = (n_log + max_s - 1) / max_s;
   int basev = n_log / k, extra = n_log % k;
   for (int i = 0; i < k; i++) S[i] = basev + (i < extra ? 1 : 0);
   return k;
@@ -594,10 +612,11 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
   // memory; register-only radix-2^k passes (v1) otherwise, and always when the caller asks for Radix2.
   int maxr = (cfg->ext_ntt_algorithm == B200_NTT_ALG_RADIX2) ? 1 : (F::N >= 12 ? 3 : 4);
   if (const char* ev = getenv("B200_NTT_MAXR")) maxr = std::max(1, std::min(4, atoi(ev)));
-  bool use_tiles = (cfg->ext_ntt_algorithm != B200_NTT_ALG_RADIX2) && !cfg->columns_batch && n_log >= 5 && total >= (uint64_t)TILE && F::N <= 12;
+  bool use_tiles = (cfg->ext_ntt_algorithm != B200_NTT_ALG_RADIX2) && !cfg->columns_batch && n_log >= 5 &&
+                   total >= ((uint64_t)1 << TileCfg<F>::TILE_LOG) && F::N <= 12;
   if (const char* ev = getenv("B200_NTT_TILES")) use_tiles = use_tiles && atoi(ev) != 0;
   int radices[32];
-  const int npass = use_tiles ? plan_tile_passes(n_log, radices) : plan_passes(n_log, maxr, radices);
+  const int npass = use_tiles ? plan_tile_passes(n_log, TileCfg<F>::MAX_S, radices) : plan_passes(n_log, maxr, radices);
 
   PassParams p;
   memset(&p, 0, sizeof(p));

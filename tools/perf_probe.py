@@ -60,6 +60,22 @@ def main():
                     best, med = ev_time(lambda: ib.ntt(ib.Field.BN254_FR, x, n, d, cfg(), y), reps=5)
                     print(f"ntt bn254 2^{logn} x{batch:5d} {ordering.name} {d.name:9s} best {best:8.3f} ms  {n * batch / best / 1e6:8.3f} Gelem/s  {n*batch*64/best/1e6:8.1f} GB/s(alg)", flush=True)
         ib.ntt_release_domain(ib.Field.BN254_FR)
+    if which in ("all", "bb"):
+        fp = utils.field_params("babybear")
+        F = ib.Field.BABYBEAR
+        dom = min(max_log, 27)
+        ib.ntt_init_domain(F, utils.to_limbs([pow(fp["rou"], 1 << (fp["two_adicity"] - dom), fp["p"])], 1)[0])
+        for logn in range(16, dom + 1, 2 if dom % 2 == 0 else 1):
+            if logn not in (16, 20, 24, dom): continue
+            n = 1 << logn
+            batch = max(1, (1 << 28) >> logn)
+            x = torch.randint(0, 0x78000001, (n * batch,), dtype=torch.int64, device="cuda").to(torch.int32).contiguous()
+            y = ib.device_empty(n * batch)
+            for ordering in (ib.Ordering.kNN, ib.Ordering.kNR):
+                cfg = lambda: ib.NTTConfig(batch_size=batch, ordering=ordering, is_async=True)
+                best, med = ev_time(lambda: ib.ntt(F, x, n, ib.NTTDir.kForward, cfg(), y), reps=5)
+                print(f"ntt babybear 2^{logn} x{batch:5d} {ordering.name} fwd best {best:8.3f} ms  {n * batch / best / 1e6:8.3f} Gelem/s  {n*batch*8/best/1e6:8.1f} GB/s(alg)", flush=True)
+        ib.ntt_release_domain(F)
     if which in ("all", "vec"):
         n = 1 << 24
         a, b = rand_scalars_dev(n), rand_scalars_dev(n)
