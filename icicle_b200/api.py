@@ -436,6 +436,45 @@ def vector_product(field, a, size, config=None, output=None):
     return output
 
 
+def highest_non_zero_idx(field, a, size, config=None):
+    cfg = copy.copy(config) if config else VecOpsConfig()
+    ap, a_dev, _ka = _ptr(a)
+    cfg.is_a_on_device = a_dev
+    cfg.is_result_on_device = False
+    out = np.zeros(cfg.batch_size, dtype=np.int64)
+    c = cfg._c()
+    check(lib.b200_highest_non_zero_idx(int(field), ap, int(size), C.byref(c), out.ctypes.data), "highest_non_zero_idx")
+    return out
+
+
+def poly_eval(field, coeffs, coeffs_size, domain, domain_size, config=None, output=None):
+    cfg = copy.copy(config) if config else VecOpsConfig()
+    cp, c_dev, _kc = _ptr(coeffs)
+    dp, d_dev, _kd = _ptr(domain)
+    cfg.is_a_on_device, cfg.is_b_on_device = c_dev, d_dev
+    if output is None:
+        output = _out_like(field, domain_size * cfg.batch_size, cfg.is_result_on_device)
+    op, o_dev, _ko = _ptr(output)
+    cfg.is_result_on_device = o_dev
+    c = cfg._c()
+    check(lib.b200_poly_eval(int(field), cp, int(coeffs_size), dp, int(domain_size), C.byref(c), op), "poly_eval")
+    return output
+
+
+def poly_division(field, numerator, numerator_size, denominator, denominator_size, q_size, r_size, config=None):
+    """Returns (q, r) host arrays (host inputs) -- device variant through the C ABI directly."""
+    cfg = copy.copy(config) if config else VecOpsConfig()
+    n_p, n_dev, _kn = _ptr(numerator)
+    d_p, d_dev, _kd = _ptr(denominator)
+    cfg.is_a_on_device, cfg.is_b_on_device, cfg.is_result_on_device = n_dev, d_dev, False
+    q = np.zeros((q_size * cfg.batch_size, field_limbs(field)), dtype=np.uint32)
+    r = np.zeros((r_size * cfg.batch_size, field_limbs(field)), dtype=np.uint32)
+    c = cfg._c()
+    check(lib.b200_poly_division(int(field), n_p, int(numerator_size), d_p, int(denominator_size), C.byref(c), q.ctypes.data, int(q_size),
+                                 r.ctypes.data, int(r_size)), "poly_division")
+    return q, r
+
+
 def convert_montgomery(field, a, size, is_into, config=None, output=None):
     cfg = config or VecOpsConfig()
     fn, ap, op, c, output = _unary("b200_convert_montgomery", field, a, size * cfg.batch_size, field_limbs(field), cfg, output)

@@ -89,6 +89,9 @@ SYMBOLS = {
     "b200_vector_div": (_i, [_i, _vp, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
     "b200_vector_sum": (_i, [_i, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
     "b200_vector_product": (_i, [_i, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
+    "b200_highest_non_zero_idx": (_i, [_i, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
+    "b200_poly_eval": (_i, [_i, _vp, _u64, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
+    "b200_poly_division": (_i, [_i, _vp, _u64, _vp, _u64, C.POINTER(VecOpsConfigC), _vp, _u64, _vp, _u64]),
     "b200_convert_montgomery": (_i, [_i, _vp, _u64, _i, C.POINTER(VecOpsConfigC), _vp]),
     "b200_bit_reverse": (_i, [_i, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
     "b200_matrix_transpose": (_i, [_i, _vp, _u32, _u32, C.POINTER(VecOpsConfigC), _vp]),

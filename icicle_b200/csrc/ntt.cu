@@ -158,6 +158,23 @@ __global__ void k_coset_setup(const uint32_t* g_std, int invert, uint32_t* pw)
   }
 }
 
+
+// Twiddle w^ex in Montgomery form.  Multi-limb fields read the domain table directly.  For the 4-byte fields a gathered
+// 4-byte read costs a whole 32-byte DRAM sector (8x amplification on an HBM-bound transform), so the exponent is split:
+// w^ex = w^(ex & ~0x3fff) * w^(ex & 0x3fff) -- both factors come from cache-resident slices of the same table (the first
+// 2^14 entries, and one entry per 64 KiB), at the price of one extra single-limb Montgomery product.
+template <class F>
+__device__ __forceinline__ F load_twiddle(const uint32_t* __restrict__ tw, uint64_t ex)
+{
+  if constexpr (F::N == 1) {
+    F lo = load_fp<F>(tw + (ex & 0x3fffull));
+    if (ex < 0x4000ull) return lo;
+    return load_fp<F>(tw + (ex & ~0x3fffull)) * lo;
+  } else {
+    return load_fp<F>(tw + ex * F::N);
+  }
+}
+
 template <class F, int LOGR>
 __global__ void __launch_bounds__(128) k_ntt_pass(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassParams p)
 {
@@ -203,7 +220,7 @@ __global__ void __launch_bounds__(128) k_ntt_pass(const uint32_t* __restrict__ s
       if (!trivial) {
         uint64_t ex = ((((uint64_t)j) << lo) | low) << sh;
         if (p.inverse) ex = (0 - ex) & dom_mask;
-        w = load_fp<F>(p.tw + ex * F::N);
+        w = load_twiddle<F>(p.tw, ex);
       }
 #pragma unroll
       for (int g = 0; g < (R >> (t + 1)); g++) {
@@ -300,7 +317,7 @@ __device__ __forceinline__ void tile_round(F (&e)[1 << LOGE], const PassParams& 
           const uint64_t j = ((uint64_t)kk << a) | mlo[g]; // m mod 2^(a+i)
           uint64_t ex = ((j << p.lo) | low[g]) << sh;
           if (p.inverse) ex = (0 - ex) & dom_mask;
-          w = load_fp<F>(p.tw + ex * F::N);
+          w = load_twiddle<F>(p.tw, ex);
         }
 #pragma unroll
         for (int up = 0; up < (1 << (Q - 1 - i)); up++) {

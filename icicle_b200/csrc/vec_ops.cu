@@ -343,6 +343,173 @@ int reduce_impl(bool product, const void* a, uint64_t size, const b200_vec_ops_c
   return finish_out(out, dout, (size_t)batch * F::BYTES, cfg->is_result_on_device, cfg->is_async, s);
 }
 
+// highest_non_zero_idx (cpu_vec_ops.cpp:600-633): out[b] = max { i : a[b][i] != 0 }, or -1 for the zero vector
+template <class F>
+__global__ void __launch_bounds__(256) k_highest_nonzero(const uint32_t* __restrict__ a, uint64_t size, uint32_t batch, bool columns, long long* out)
+{
+  const uint64_t total = size * batch;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t b = columns ? (t % batch) : (t / size);
+    const uint64_t i = columns ? (t / batch) : (t % size);
+    if (!load_fp<F>(a + t * F::N).is_zero()) atomicMax(out + b, (long long)i);
+  }
+}
+__global__ void k_fill_i64(long long* p, long long v, uint32_t n)
+{
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// poly_eval, Horner per (batch, domain point) (cpu_vec_ops.cpp:676-705): evals[b][j] = sum_i coeffs[b][i] * domain[j]^i
+template <class F>
+__global__ void __launch_bounds__(128) k_poly_eval(
+  const uint32_t* __restrict__ coeffs, uint64_t coeffs_size, const uint32_t* __restrict__ domain, uint64_t domain_size, uint32_t batch,
+  bool columns, uint32_t* __restrict__ evals)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= domain_size * batch) return;
+  const uint64_t b = columns ? (t % batch) : (t / domain_size);
+  const uint64_t j = columns ? (t / batch) : (t % domain_size);
+  const uint64_t stride = columns ? batch : 1;
+  const uint32_t* c = coeffs + (columns ? b : b * coeffs_size) * F::N;
+  const F x = load_fp<F>(domain + j * F::N).to_mont(); // x*R: mont_mul(acc, x*R) = acc*x stays in standard form
+  F acc = load_fp<F>(c + (coeffs_size - 1) * stride * F::N);
+  for (int64_t i = (int64_t)coeffs_size - 2; i >= 0; --i) acc = acc * x + load_fp<F>(c + (uint64_t)i * stride * F::N);
+  store_fp<F>(evals + t * F::N, acc);
+}
+
+// school-book polynomial division, one CTA per batch element (cpu_vec_ops.cpp:708-777).  r must already hold the numerator
+// (zero padded to r_size); q entries of monomials that are never visited are left untouched, like the reference.
+template <class F>
+__global__ void __launch_bounds__(256) k_poly_divide(
+  const uint32_t* __restrict__ den, uint64_t den_size, uint32_t batch, bool columns, const long long* __restrict__ num_deg,
+  const long long* __restrict__ den_deg, uint32_t* __restrict__ q, uint64_t q_size, uint32_t* __restrict__ r, uint64_t r_size)
+{
+  __shared__ uint32_t s_coef[F::N];
+  __shared__ long long s_deg;
+  const uint32_t b = blockIdx.x;
+  const uint64_t stride = columns ? batch : 1;
+  const uint32_t* d = den + (columns ? (uint64_t)b : (uint64_t)b * den_size) * F::N;
+  uint32_t* qq = q + (columns ? (uint64_t)b : (uint64_t)b * q_size) * F::N;
+  uint32_t* rr = r + (columns ? (uint64_t)b : (uint64_t)b * r_size) * F::N;
+  const long long deg_b = den_deg[b];
+  if (deg_b < 0) return; // division by the zero polynomial: leave outputs as they are
+  __shared__ uint32_t s_lcinv[F::N];
+  if (threadIdx.x == 0) {
+    F inv = fermat_inv_mont(load_fp<F>(d + (uint64_t)deg_b * stride * F::N).to_mont()); // lc(b)^-1 * R
+#pragma unroll
+    for (int l = 0; l < F::N; l++) s_lcinv[l] = inv.v[l];
+    s_deg = num_deg[b];
+  }
+  __syncthreads();
+  long long deg_r = s_deg;
+  while (deg_r >= deg_b) {
+    const long long mono = deg_r - deg_b;
+    if (threadIdx.x == 0) {
+      F inv;
+#pragma unroll
+      for (int l = 0; l < F::N; l++) inv.v[l] = s_lcinv[l];
+      F coef = load_fp<F>(rr + (uint64_t)deg_r * stride * F::N) * inv; // lc(r)/lc(b), standard form
+      store_fp<F>(qq + (uint64_t)mono * stride * F::N, coef);
+      F cm = coef.to_mont();
+#pragma unroll
+      for (int l = 0; l < F::N; l++) s_coef[l] = cm.v[l];
+    }
+    __syncthreads();
+    F cm;
+#pragma unroll
+    for (int l = 0; l < F::N; l++) cm.v[l] = s_coef[l];
+    for (long long i = mono + threadIdx.x; i <= deg_r; i += blockDim.x) {
+      F bc = load_fp<F>(d + (uint64_t)(i - mono) * stride * F::N);
+      F rv = load_fp<F>(rr + (uint64_t)i * stride * F::N);
+      store_fp<F>(rr + (uint64_t)i * stride * F::N, rv - cm * bc);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { // new degree of r: the leading term cancelled exactly, scan down for the next non-zero
+      long long k = deg_r - 1;
+      while (k >= 0 && load_fp<F>(rr + (uint64_t)k * stride * F::N).is_zero()) k--;
+      s_deg = k;
+    }
+    __syncthreads();
+    deg_r = s_deg;
+  }
+}
+
+template <class F>
+int highest_nonzero_impl(const void* a, uint64_t size, const b200_vec_ops_config* cfg, long long* out)
+{
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  const uint32_t batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
+  if (size == 0) return B200_INVALID_ARGUMENT;
+  Scratch sa, so;
+  const void* da;
+  void* dout;
+  int err;
+  if ((err = stage_in(da, a, size * batch * F::BYTES, cfg->is_a_on_device, s, sa))) return err;
+  if ((err = stage_out(dout, out, (size_t)batch * 8, cfg->is_result_on_device, s, so))) return err;
+  k_fill_i64<<<(batch + 255) / 256, 256, 0, s>>>((long long*)dout, -1, batch); B200_LAUNCHED(1);
+  k_highest_nonzero<F><<<grid_for(size * batch), VEC_THREADS, 0, s>>>((const uint32_t*)da, size, batch, cfg->columns_batch, (long long*)dout); B200_LAUNCHED(1);
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  return finish_out(out, dout, (size_t)batch * 8, cfg->is_result_on_device, cfg->is_async, s);
+}
+
+template <class F>
+int poly_eval_impl(const void* coeffs, uint64_t coeffs_size, const void* domain, uint64_t domain_size, const b200_vec_ops_config* cfg, void* evals)
+{
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  const uint32_t batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
+  if (coeffs_size == 0 || domain_size == 0) return B200_INVALID_ARGUMENT;
+  Scratch sc, sd, so;
+  const void *dc, *dd;
+  void* dout;
+  int err;
+  if ((err = stage_in(dc, coeffs, coeffs_size * batch * F::BYTES, cfg->is_a_on_device, s, sc))) return err;
+  if ((err = stage_in(dd, domain, domain_size * F::BYTES, cfg->is_b_on_device, s, sd))) return err;
+  const size_t obytes = domain_size * batch * F::BYTES;
+  if ((err = stage_out(dout, evals, obytes, cfg->is_result_on_device, s, so))) return err;
+  const uint64_t threads = domain_size * batch;
+  k_poly_eval<F><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(
+    (const uint32_t*)dc, coeffs_size, (const uint32_t*)dd, domain_size, batch, cfg->columns_batch, (uint32_t*)dout); B200_LAUNCHED(1);
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  return finish_out(evals, dout, obytes, cfg->is_result_on_device, cfg->is_async, s);
+}
+
+template <class F>
+int poly_divide_impl(const void* num, uint64_t num_size, const void* den, uint64_t den_size, const b200_vec_ops_config* cfg, void* q,
+                     uint64_t q_size, void* r, uint64_t r_size)
+{
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  const uint32_t batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
+  if (num_size == 0 || den_size == 0 || r_size < num_size) return B200_INVALID_ARGUMENT;
+  Scratch sn, sd, sq, sr, sdeg;
+  const void *dn, *dd;
+  void *dq, *dr;
+  int err;
+  if ((err = stage_in(dn, num, num_size * batch * F::BYTES, cfg->is_a_on_device, s, sn))) return err;
+  if ((err = stage_in(dd, den, den_size * batch * F::BYTES, cfg->is_b_on_device, s, sd))) return err;
+  const size_t qb = q_size * batch * F::BYTES, rb = r_size * batch * F::BYTES;
+  if ((err = stage_out(dq, q, qb, cfg->is_result_on_device, s, sq))) return err;
+  if ((err = stage_out(dr, r, rb, cfg->is_result_on_device, s, sr))) return err;
+  if (!cfg->is_result_on_device) B200_CUDA_TRY(cudaMemcpyAsync(dq, q, qb, cudaMemcpyHostToDevice, s), B200_COPY_FAILED); // keep untouched entries
+  if ((err = sdeg.alloc((size_t)batch * 16, s))) return err;
+  long long* ndeg = sdeg.as<long long>();
+  long long* ddeg = ndeg + batch;
+  // r <- numerator zero-padded to r_size (row or column batches keep their layout because r_size may exceed num_size only for rows)
+  B200_CUDA_TRY(cudaMemsetAsync(dr, 0, rb, s), B200_UNKNOWN_ERROR);
+  if (cfg->columns_batch || r_size == num_size) {
+    B200_CUDA_TRY(cudaMemcpyAsync(dr, dn, num_size * batch * F::BYTES, cudaMemcpyDeviceToDevice, s), B200_COPY_FAILED);
+  } else {
+    B200_CUDA_TRY(cudaMemcpy2DAsync(dr, r_size * F::BYTES, dn, num_size * F::BYTES, num_size * F::BYTES, batch, cudaMemcpyDeviceToDevice, s), B200_COPY_FAILED);
+  }
+  k_fill_i64<<<(2 * batch + 255) / 256, 256, 0, s>>>(ndeg, -1, 2 * batch); B200_LAUNCHED(1);
+  k_highest_nonzero<F><<<grid_for(num_size * batch), VEC_THREADS, 0, s>>>((const uint32_t*)dn, num_size, batch, cfg->columns_batch, ndeg); B200_LAUNCHED(1);
+  k_highest_nonzero<F><<<grid_for(den_size * batch), VEC_THREADS, 0, s>>>((const uint32_t*)dd, den_size, batch, cfg->columns_batch, ddeg); B200_LAUNCHED(1);
+  k_poly_divide<F><<<batch, 256, 0, s>>>((const uint32_t*)dd, den_size, batch, cfg->columns_batch, ndeg, ddeg, (uint32_t*)dq, q_size, (uint32_t*)dr, r_size); B200_LAUNCHED(1);
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  if (!cfg->is_result_on_device) B200_CUDA_TRY(cudaMemcpyAsync(q, dq, qb, cudaMemcpyDeviceToHost, s), B200_COPY_FAILED);
+  return finish_out(r, dr, rb, cfg->is_result_on_device, cfg->is_async, s);
+}
+
 int curve_base_field(int curve, int* coords_per_point_factor)
 {
   *coords_per_point_factor = 1;
@@ -399,6 +566,27 @@ int b200_vector_product(int field, const void* a, uint64_t size, const b200_vec_
 {
   if (!cfg || !a || !out) return B200_INVALID_POINTER;
   B200_DISPATCH_FIELD(field, return reduce_impl<F>(true, a, size, cfg, out));
+  return B200_INVALID_ARGUMENT;
+}
+
+int b200_highest_non_zero_idx(int field, const void* a, uint64_t size, const b200_vec_ops_config* cfg, int64_t* out_idx)
+{
+  if (!cfg || !a || !out_idx) return B200_INVALID_POINTER;
+  B200_DISPATCH_FIELD(field, return highest_nonzero_impl<F>(a, size, cfg, (long long*)out_idx));
+  return B200_INVALID_ARGUMENT;
+}
+int b200_poly_eval(int field, const void* coeffs, uint64_t coeffs_size, const void* domain, uint64_t domain_size, const b200_vec_ops_config* cfg,
+                   void* evals)
+{
+  if (!cfg || !coeffs || !domain || !evals) return B200_INVALID_POINTER;
+  B200_DISPATCH_FIELD(field, return poly_eval_impl<F>(coeffs, coeffs_size, domain, domain_size, cfg, evals));
+  return B200_INVALID_ARGUMENT;
+}
+int b200_poly_division(int field, const void* numerator, uint64_t numerator_size, const void* denominator, uint64_t denominator_size,
+                       const b200_vec_ops_config* cfg, void* q_out, uint64_t q_size, void* r_out, uint64_t r_size)
+{
+  if (!cfg || !numerator || !denominator || !q_out || !r_out) return B200_INVALID_POINTER;
+  B200_DISPATCH_FIELD(field, return poly_divide_impl<F>(numerator, numerator_size, denominator, denominator_size, cfg, q_out, q_size, r_out, r_size));
   return B200_INVALID_ARGUMENT;
 }
 

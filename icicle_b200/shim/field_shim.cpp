@@ -10,6 +10,9 @@
 #include "icicle/backend/vec_ops_backend.h"
 #include "icicle/fields/field_config.h"
 #ifdef NTT
+  #include "icicle/backend/polynomial_backend.h"
+  #include "icicle/polynomials/default_backend/default_poly_context.h"
+  #include "icicle/polynomials/default_backend/default_poly_backend.h"
   #include "icicle/ntt.h"
   #include "icicle/backend/ntt_backend.h"
   #include "icicle/backend/ntt_config.h"
@@ -68,6 +71,23 @@ namespace {
   {
     b200_vec_ops_config c = to_c(config);
     return to_err(b200_vector_product(FIELD, a, size, &c, out));
+  }
+  eIcicleError highest_idx(const Device&, const scalar_t* in, uint64_t size, const VecOpsConfig& config, int64_t* out_idx)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_highest_non_zero_idx(FIELD, in, size, &c, out_idx));
+  }
+  eIcicleError poly_eval(const Device&, const scalar_t* coeffs, uint64_t coeffs_size, const scalar_t* domain, uint64_t domain_size,
+                         const VecOpsConfig& config, scalar_t* evals)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_poly_eval(FIELD, coeffs, coeffs_size, domain, domain_size, &c, evals));
+  }
+  eIcicleError poly_div(const Device&, const scalar_t* num, uint64_t num_size, const scalar_t* den, uint64_t den_size, const VecOpsConfig& config,
+                        scalar_t* q, uint64_t q_size, scalar_t* r, uint64_t r_size)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_poly_division(FIELD, num, num_size, den, den_size, &c, q, q_size, r, r_size));
   }
   eIcicleError convert_mont(const Device&, const scalar_t* in, uint64_t size, bool is_into, const VecOpsConfig& config, scalar_t* out)
   {
@@ -132,6 +152,9 @@ REGISTER_VECTOR_INV_BACKEND(B200_DEVICE_TYPE, vec_inv);
 REGISTER_VECTOR_DIV_BACKEND(B200_DEVICE_TYPE, vec_div);
 REGISTER_VECTOR_SUM_BACKEND(B200_DEVICE_TYPE, vec_sum);
 REGISTER_VECTOR_PRODUCT_BACKEND(B200_DEVICE_TYPE, vec_product);
+REGISTER_HIGHEST_NON_ZERO_IDX_BACKEND(B200_DEVICE_TYPE, highest_idx);
+REGISTER_POLYNOMIAL_EVAL(B200_DEVICE_TYPE, poly_eval);
+REGISTER_POLYNOMIAL_DIVISION(B200_DEVICE_TYPE, poly_div);
 REGISTER_CONVERT_MONTGOMERY_BACKEND(B200_DEVICE_TYPE, convert_mont);
 REGISTER_BIT_REVERSE_BACKEND(B200_DEVICE_TYPE, bit_rev);
 REGISTER_SLICE_BACKEND(B200_DEVICE_TYPE, slice_op);
@@ -141,4 +164,24 @@ REGISTER_NTT_BACKEND(B200_DEVICE_TYPE, ntt_impl);
 REGISTER_NTT_INIT_DOMAIN_BACKEND(B200_DEVICE_TYPE, ntt_init);
 REGISTER_NTT_RELEASE_DOMAIN_BACKEND(B200_DEVICE_TYPE, ntt_release);
 REGISTER_NTT_GET_ROU_FROM_DOMAIN_BACKEND(B200_DEVICE_TYPE, ntt_rou);
+
+// Polynomial API on the device: the reference's default polynomial backend is device-agnostic -- it only
+// calls ntt / vec-ops / icicle_malloc on the active device -- so registering its factory for our device type is all that is
+// needed (model: icicle/backend/cpu/src/polynomials/cpu_polynomial_backend.cpp:13-37).
+namespace polynomials {
+  template <typename C = scalar_t, typename D = C, typename I = C>
+  class B200PolynomialFactory : public AbstractPolynomialFactory<C, D, I>
+  {
+  public:
+    std::shared_ptr<IPolynomialContext<C, D, I>> create_context() override
+    {
+      return std::make_shared<icicle::DefaultPolynomialContext<C, D, I>>(nullptr);
+    }
+    std::shared_ptr<IPolynomialBackend<C, D, I>> create_backend() override
+    {
+      return std::make_shared<icicle::DefaultPolynomialBackend<C, D, I>>(nullptr);
+    }
+  };
+  REGISTER_SCALAR_POLYNOMIAL_FACTORY_BACKEND(B200_DEVICE_TYPE, B200PolynomialFactory<scalar_t>)
+} // namespace polynomials
 #endif

@@ -206,6 +206,15 @@ B200_API int b200_vector_div(int field, const void* a, const void* b, uint64_t s
 /* vector_sum / vector_product: one output element per batch (VectorReduceOpImpl, vec_ops_backend.h:22-23,156,166; cpu_vec_ops.cpp:428-490) */
 B200_API int b200_vector_sum(int field, const void* a, uint64_t size, const b200_vec_ops_config* cfg, void* out);
 B200_API int b200_vector_product(int field, const void* a, uint64_t size, const b200_vec_ops_config* cfg, void* out);
+/* the three vec-ops the reference's device-agnostic Polynomial backend needs on top of the above:
+ * highest_non_zero_idx (vec_ops_backend.h:54-55,236; cpu_vec_ops.cpp:600-633) -- out_idx[batch], -1 for the zero vector
+ * poly_eval  (vec_ops_backend.h:64-71,246; cpu_vec_ops.cpp:676-705) -- Horner, coefficient batches x one domain
+ * poly_division (vec_ops_backend.h:73-83,256; cpu_vec_ops.cpp:708-777) -- school-book long division, q and r out */
+B200_API int b200_highest_non_zero_idx(int field, const void* a, uint64_t size, const b200_vec_ops_config* cfg, int64_t* out_idx);
+B200_API int b200_poly_eval(int field, const void* coeffs, uint64_t coeffs_size, const void* domain, uint64_t domain_size,
+                            const b200_vec_ops_config* cfg, void* evals);
+B200_API int b200_poly_division(int field, const void* numerator, uint64_t numerator_size, const void* denominator, uint64_t denominator_size,
+                                const b200_vec_ops_config* cfg, void* q_out, uint64_t q_size, void* r_out, uint64_t r_size);
 /* convert_montgomery (vec_ops_backend.h ConvertMontgomery; cpu_vec_ops.cpp) */
 B200_API int b200_convert_montgomery(int field, const void* in, uint64_t size, int is_into, const b200_vec_ops_config* cfg, void* out);
 /* bit_reverse (cpu_vec_ops.cpp:535-575): out[i] = in[bitrev(i)], size must be a power of two */

@@ -127,3 +127,54 @@ def test_ntt_and_vec_ops_main_vs_ref_device(r):
     r.ntt_release_domain()
     r.set_device("CPU", 0)
     r.ntt_release_domain()
+
+
+def test_polynomial_api_on_device(r):
+    """the reference's Polynomial class (device-agnostic default backend) running on our device through
+    the registered factory + ntt + vec-ops; checked against the CPU device (icicle/tests/test_polynomial_api.cpp flows)."""
+    f = r.field
+    logn = 10
+    r.set_device("CPU", 0)
+    root = r.get_root_of_unity(1 << (logn + 3))
+    a_c, b_c = r.generate_scalars(1 << logn), r.generate_scalars(1 << (logn - 1))
+    dom = r.generate_scalars(16)
+    f.bn254_polynomial_create_from_coefficients.restype = C.c_void_p
+    f.bn254_polynomial_create_from_coefficients.argtypes = [C.c_void_p, C.c_size_t]
+    for fn in ("multiply", "add", "subtract", "quotient", "remainder"):
+        getattr(f, f"bn254_polynomial_{fn}").restype = C.c_void_p
+        getattr(f, f"bn254_polynomial_{fn}").argtypes = [C.c_void_p, C.c_void_p]
+    f.bn254_polynomial_degree.restype = C.c_int64
+    f.bn254_polynomial_degree.argtypes = [C.c_void_p]
+    f.bn254_polynomial_copy_coeffs_range.restype = C.c_int64
+    f.bn254_polynomial_copy_coeffs_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+    f.bn254_polynomial_evaluate_on_domain.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    f.bn254_polynomial_delete.argtypes = [C.c_void_p]
+
+    def run(device):
+        r.set_device(device, 0)
+        r.ntt_init_domain(root)
+        A = f.bn254_polynomial_create_from_coefficients(a_c.ctypes.data, a_c.shape[0])
+        B = f.bn254_polynomial_create_from_coefficients(b_c.ctypes.data, b_c.shape[0])
+        out = {}
+        for name in ("multiply", "add", "subtract", "quotient", "remainder"):
+            P = getattr(f, f"bn254_polynomial_{name}")(A, B)
+            deg = f.bn254_polynomial_degree(P)
+            coeffs = np.zeros((deg + 1, 8), dtype=np.uint32)
+            f.bn254_polynomial_copy_coeffs_range(P, coeffs.ctypes.data, 0, deg)
+            out[name] = (deg, coeffs)
+            if name == "multiply":
+                ev = np.zeros((16, 8), dtype=np.uint32)
+                f.bn254_polynomial_evaluate_on_domain(P, dom.ctypes.data, 16, ev.ctypes.data)
+                out["evals"] = (16, ev)
+            f.bn254_polynomial_delete(P)
+        f.bn254_polynomial_delete(A)
+        f.bn254_polynomial_delete(B)
+        r.ntt_release_domain()
+        return out
+
+    exp = run("CPU")
+    got = run("CUDA")
+    for k in exp:
+        assert exp[k][0] == got[k][0], k
+        assert np.array_equal(exp[k][1], got[k][1]), k
+    r.set_device("CPU", 0)

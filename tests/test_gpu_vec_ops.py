@@ -144,3 +144,30 @@ def test_vs_reference_cpu_backend():
     assert np.array_equal(ib.affine_convert_montgomery(ib.Curve.BN254_G1, pts, 300, True), r.affine_convert_montgomery(pts, 300, True))
     g2 = r.generate_affine_points(50, g2=True)
     assert np.array_equal(ib.affine_convert_montgomery(ib.Curve.BN254_G2, g2, 50, True), r.affine_convert_montgomery(g2, 50, True, g2=True))
+
+
+def test_highest_idx_poly_eval_division():
+    field, name = FIELDS[0]
+    fp = utils.field_params(name)
+    p, L = fp["p"], fp["limbs"]
+    a = common.rand_field_elems(name, 300, 31, as_ints=True)
+    a[250:] = [0] * 50
+    assert list(ib.highest_non_zero_idx(field, utils.to_limbs(a, L), 300)) == [249]
+    assert list(ib.highest_non_zero_idx(field, utils.to_limbs([0] * 10, L), 10)) == [-1]
+    coeffs = common.rand_field_elems(name, 40, 32, as_ints=True)
+    dom = common.rand_field_elems(name, 9, 33, as_ints=True)
+    ev = utils.from_limbs(ib.poly_eval(field, utils.to_limbs(coeffs, L), 40, utils.to_limbs(dom, L), 9))
+    assert ev == [sum(c * pow(x, i, p) for i, c in enumerate(coeffs)) % p for x in dom]
+    # division: num = q*den + r with deg r < deg den
+    den = common.rand_field_elems(name, 12, 34, as_ints=True)
+    q_true = common.rand_field_elems(name, 20, 35, as_ints=True)
+    r_true = common.rand_field_elems(name, 11, 36, as_ints=True)
+    num = [0] * 31
+    for i, x in enumerate(q_true):
+        for j, y in enumerate(den):
+            num[i + j] = (num[i + j] + x * y) % p
+    for i, x in enumerate(r_true):
+        num[i] = (num[i] + x) % p
+    q, rr = ib.poly_division(field, utils.to_limbs(num, L), 31, utils.to_limbs(den, L), 12, 20, 31)
+    assert utils.from_limbs(q) == q_true
+    assert utils.from_limbs(rr)[:11] == r_true and not any(utils.from_limbs(rr)[11:])
