@@ -453,10 +453,10 @@ struct TileCfg {
   static constexpr int MAX_S = (F::N == 1) ? 10 : 9; // stages per pass
 };
 
-template <class F>
-int launch_tile_pass(const uint32_t* src, uint32_t* dst, const PassParams& p, int S, cudaStream_t s)
+template <class F, int LOGE, int LOGT>
+int launch_tile_pass_geom(const uint32_t* src, uint32_t* dst, const PassParams& p, int S, cudaStream_t s)
 {
-  constexpr int LOGE = TileCfg<F>::LOGE, LOGT = TileCfg<F>::LOGT, TILE_LOG = TileCfg<F>::TILE_LOG;
+  constexpr int TILE_LOG = LOGE + LOGT;
   const uint64_t total = ((uint64_t)1 << p.n_log) * p.batch;
   const uint64_t total_cols = total >> S;
   const uint32_t C = 1u << (TILE_LOG - S);
@@ -466,6 +466,45 @@ int launch_tile_pass(const uint32_t* src, uint32_t* dst, const PassParams& p, in
   k_ntt_tile<F, LOGE, LOGT><<<(unsigned)blocks, 1 << LOGT, smem, s>>>(src, dst, p, (uint32_t)S, total_cols); B200_LAUNCHED(1);
   B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
   return B200_SUCCESS;
+}
+
+// developer knob: B200_NTT_GEOM="<loge><logt>" selects an alternative tile geometry for the 8-limb fields (tuning experiments)
+inline int tile_geom_override()
+{
+  static int cached = -1;
+  if (cached < 0) {
+    const char* ev = getenv("B200_NTT_GEOM");
+    cached = ev ? atoi(ev) : 0;
+  }
+  return cached;
+}
+
+template <class F>
+int tile_log_for()
+{
+  if constexpr (F::N == 8) {
+    switch (tile_geom_override()) {
+    case 28: return 10;
+    case 29: return 11;
+    case 37: return 10;
+    default: break;
+    }
+  }
+  return TileCfg<F>::TILE_LOG;
+}
+
+template <class F>
+int launch_tile_pass(const uint32_t* src, uint32_t* dst, const PassParams& p, int S, cudaStream_t s)
+{
+  if constexpr (F::N == 8) {
+    switch (tile_geom_override()) {
+    case 28: return launch_tile_pass_geom<F, 2, 8>(src, dst, p, S, s);
+    case 29: return launch_tile_pass_geom<F, 2, 9>(src, dst, p, S, s);
+    case 37: return launch_tile_pass_geom<F, 3, 7>(src, dst, p, S, s);
+    default: break;
+    }
+  }
+  return launch_tile_pass_geom<F, TileCfg<F>::LOGE, TileCfg<F>::LOGT>(src, dst, p, S, s);
 }
 
 // split n_log stages into tile passes of at most max_s stages (as few passes as possible, sizes as even as possible)
@@ -630,7 +669,7 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
   int maxr = (cfg->ext_ntt_algorithm == B200_NTT_ALG_RADIX2) ? 1 : (F::N >= 12 ? 3 : 4);
   if (const char* ev = getenv("B200_NTT_MAXR")) maxr = std::max(1, std::min(4, atoi(ev)));
   bool use_tiles = (cfg->ext_ntt_algorithm != B200_NTT_ALG_RADIX2) && !cfg->columns_batch && n_log >= 5 &&
-                   total >= ((uint64_t)1 << TileCfg<F>::TILE_LOG) && F::N <= 12;
+                   total >= ((uint64_t)1 << tile_log_for<F>()) && F::N <= 12;
   if (const char* ev = getenv("B200_NTT_TILES")) use_tiles = use_tiles && atoi(ev) != 0;
   int radices[32];
   const int npass = use_tiles ? plan_tile_passes(n_log, TileCfg<F>::MAX_S, radices) : plan_passes(n_log, maxr, radices);
