@@ -291,7 +291,7 @@ __device__ __forceinline__ void tile_store(uint32_t* sm, uint32_t e, const F& a)
 // 2^Q.  mlo[g] = (m mod 2^a) of group g's elements, low[g] = the untransformed index below the digit (twiddle argument).
 template <class F, int LOGE, int Q>
 __device__ __forceinline__ void tile_round(F (&e)[1 << LOGE], const PassParams& p, uint32_t a, const uint32_t* eid, uint32_t logC, uint64_t col0,
-                                           uint64_t rmask)
+                                           uint64_t rmask, const uint32_t* twsm, uint32_t S)
 {
   constexpr int G = (1 << LOGE) >> Q;
   const uint64_t dom_mask = (1ull << p.dom_log) - 1;
@@ -307,7 +307,10 @@ __device__ __forceinline__ void tile_round(F (&e)[1 << LOGE], const PassParams& 
   for (int i = Q - 1; i >= 0; --i) {
     const uint32_t s = p.lo + a + i; // global stage
     const uint32_t sh = p.dom_log - (s + 1);
-    const bool trivial = (s == 0);
+    // kFourStep (4-byte fields): the pass runs a PURE 2^S-point sub-NTT whose twiddles w_{2^S}^j sit in shared memory; the
+    // column-dependent factor is applied once per element when the pass stores (see k_ntt_tile).  Otherwise: exact DIF twiddles.
+    constexpr bool kFourStep = (F::N == 1);
+    const bool trivial = kFourStep ? (a + i == 0) : (s == 0);
 #pragma unroll
     for (int g = 0; g < G; g++) {
 #pragma unroll
@@ -315,9 +318,13 @@ __device__ __forceinline__ void tile_round(F (&e)[1 << LOGE], const PassParams& 
         F w;
         if (!trivial) {
           const uint64_t j = ((uint64_t)kk << a) | mlo[g]; // m mod 2^(a+i)
-          uint64_t ex = ((j << p.lo) | low[g]) << sh;
-          if (p.inverse) ex = (0 - ex) & dom_mask;
-          w = load_twiddle<F>(p.tw, ex);
+          if constexpr (kFourStep) {
+            w.v[0] = twsm[(uint32_t)j << (S - 1 - (a + i))];
+          } else {
+            uint64_t ex = ((j << p.lo) | low[g]) << sh;
+            if (p.inverse) ex = (0 - ex) & dom_mask;
+            w = load_twiddle<F>(p.tw, ex);
+          }
         }
 #pragma unroll
         for (int up = 0; up < (1 << (Q - 1 - i)); up++) {
@@ -336,15 +343,15 @@ __device__ __forceinline__ void tile_round(F (&e)[1 << LOGE], const PassParams& 
 template <class F, int LOGE, int Q>
 struct RoundDispatch {
   static __device__ __forceinline__ void run(int q, F (&e)[1 << LOGE], const PassParams& p, uint32_t a, const uint32_t* eid, uint32_t logC,
-                                             uint64_t col0, uint64_t rmask)
+                                             uint64_t col0, uint64_t rmask, const uint32_t* twsm, uint32_t S)
   {
-    if (q == Q) tile_round<F, LOGE, Q>(e, p, a, eid, logC, col0, rmask);
-    else RoundDispatch<F, LOGE, Q - 1>::run(q, e, p, a, eid, logC, col0, rmask);
+    if (q == Q) tile_round<F, LOGE, Q>(e, p, a, eid, logC, col0, rmask, twsm, S);
+    else RoundDispatch<F, LOGE, Q - 1>::run(q, e, p, a, eid, logC, col0, rmask, twsm, S);
   }
 };
 template <class F, int LOGE>
 struct RoundDispatch<F, LOGE, 0> {
-  static __device__ __forceinline__ void run(int, F (&)[1 << LOGE], const PassParams&, uint32_t, const uint32_t*, uint32_t, uint64_t, uint64_t) {}
+  static __device__ __forceinline__ void run(int, F (&)[1 << LOGE], const PassParams&, uint32_t, const uint32_t*, uint32_t, uint64_t, uint64_t, const uint32_t*, uint32_t) {}
 };
 
 template <class F, int LOGE, int LOGT>
@@ -364,6 +371,18 @@ k_ntt_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassPar
   const uint64_t col0 = (uint64_t)blockIdx.x * C;
   const uint32_t rsh = n_log - S;           // rot: shift of the (top) digit being transformed
   const uint64_t rmask = (1ull << rsh) - 1; // rot: mask of everything below it
+
+  constexpr bool kFourStep = (F::N == 1);
+  uint32_t* twsm = sm + (size_t)PAD * F::N; // kFourStep: w_{2^S}^j (j < 2^(S-1)), Montgomery form, direction applied
+  if constexpr (kFourStep) {
+    const uint64_t dom_mask = (1ull << p.dom_log) - 1;
+    for (uint32_t j = T; j < (1u << (S - 1)); j += NT) {
+      uint64_t ex = (uint64_t)j << (p.dom_log - S);
+      if (p.inverse) ex = (0 - ex) & dom_mask;
+      twsm[j] = load_twiddle<F>(p.tw, ex).v[0];
+    }
+    __syncthreads();
+  }
 
   F e[E];
   int a = (int)S;
@@ -405,7 +424,7 @@ k_ntt_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassPar
       __syncthreads(); // everyone has read before anyone overwrites
     }
     // ---- butterflies ----
-    RoundDispatch<F, LOGE, LOGE>::run(q, e, p, (uint32_t)a, eid, logC, col0, rmask);
+    RoundDispatch<F, LOGE, LOGE>::run(q, e, p, (uint32_t)a, eid, logC, col0, rmask, twsm, S);
     // ---- store ----
     if (last_round) {
 #pragma unroll
@@ -414,6 +433,14 @@ k_ntt_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassPar
         const uint64_t colg = col0 + c;
         if (colg >= total_cols) continue;
         uint64_t idx;
+        if constexpr (kFourStep) {
+          if (lo > 0) { // inter-pass twiddle w_L^(l * rev_S(m)), L = 2^(lo+S), l = untransformed index below the digit
+            const uint64_t l = p.rot ? ((colg & rmask) >> p.done) : (colg & ((1ull << lo) - 1));
+            uint64_t ex = (l * (uint64_t)(__brev(m) >> (32 - S))) << (p.dom_log - (lo + S));
+            if (p.inverse) ex = (0 - ex) & ((1ull << p.dom_log) - 1);
+            e[u] = e[u] * load_twiddle<F>(p.tw, ex);
+          }
+        }
         if (p.rot) {
           const uint64_t lowfull = colg & rmask;
           const uint64_t mrev = (uint64_t)(__brev(m) >> (32 - S));
@@ -461,7 +488,7 @@ int launch_tile_pass_geom(const uint32_t* src, uint32_t* dst, const PassParams& 
   const uint64_t total_cols = total >> S;
   const uint32_t C = 1u << (TILE_LOG - S);
   const uint64_t blocks = (total_cols + C - 1) / C;
-  const size_t smem = (size_t)TileGeom<TILE_LOG>::PAD * F::N * 4;
+  const size_t smem = (size_t)TileGeom<TILE_LOG>::PAD * F::N * 4 + (F::N == 1 ? ((size_t)4 << (S > 0 ? S - 1 : 0)) : 0);
   B200_CUDA_TRY(cudaFuncSetAttribute(k_ntt_tile<F, LOGE, LOGT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), B200_UNKNOWN_ERROR);
   k_ntt_tile<F, LOGE, LOGT><<<(unsigned)blocks, 1 << LOGT, smem, s>>>(src, dst, p, (uint32_t)S, total_cols); B200_LAUNCHED(1);
   B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
