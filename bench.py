@@ -35,6 +35,11 @@ ALG_BYTES_PER_POINT = 96  # |scalar_t| + |affine_t| for BN254 G1
 ALG_BYTES_PER_NTT_ELEM = 64  # one read + one write of a 32-byte element
 IMAD_WIDE_PEAK = 9.26e12  # measured on this pool's B200 (tools/imad_bench.cu, profiles/r1_imad_microbench.txt): IMAD.WIDE.U32.X thread-instr/s
 IMAD_WIDE_PER_MADD = 10 * 140  # 8M+2S Montgomery products per mixed add x 140 IMAD(.WIDE) per 8-limb product (cuobjdump)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_accumulate launch at the headline config (2^26 points, c = 20), from
+# `ncu --set full` (profiles/r1_ncu_full_k_accumulate_2p26_raw.csv): 122.69 GB + 1.96 GB.  It is ~19x the algorithmic 6.44 GB
+# because every point (64 B) is gathered once per window (13x) and the sorted (key, index) lists are read too; the kernel
+# is integer-multiply bound (sm throughput 87 %, DRAM 10.8 % of peak), so this traffic is not what limits it.
+NCU_TRAFFIC_BYTES = {(26, 20): 124.65e9}
 
 
 def hbm_peak():
@@ -267,7 +272,7 @@ def main():
     achieved = ALG_BYTES_PER_POINT * n / (acc * 1e-3) / 1e9
     nwin = (254 + 1 + c_used - 1) // c_used
     roofline = {"bound": "hbm", "kernel": "k_accumulate<Fp<bn254_fq>>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "kernel_ms": acc,
+                "traffic": NCU_TRAFFIC_BYTES.get((args.logn, c_used)), "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "kernel_ms": acc,
                 "stage_ms": {k: round(v, 3) for k, v in stage_sum.items()},
                 "imad_frac": (n * nwin * IMAD_WIDE_PER_MADD / (acc * 1e-3)) / IMAD_WIDE_PEAK,
                 "note": "integer-multiply bound: imad_frac = (N * windows * 1400 IMAD.WIDE) / kernel time vs the measured 9.26e12 IMAD.WIDE/s"}
