@@ -355,7 +355,7 @@ struct RoundDispatch<F, LOGE, 0> {
 };
 
 template <class F, int LOGE, int LOGT>
-__global__ void __launch_bounds__(1 << LOGT, (LOGT >= 9 ? 1 : 2))
+__global__ void __launch_bounds__(1 << LOGT, (LOGT >= 9 ? 1 : (LOGT == 8 ? 2 : 4)))
 k_ntt_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassParams p, uint32_t S, uint64_t total_cols)
 {
   constexpr int E = 1 << LOGE;
@@ -517,6 +517,16 @@ int tile_log_for()
     default: break;
     }
   }
+  if constexpr (F::N == 1) {
+    switch (tile_geom_override()) {
+    case 58: return 13;
+    case 48: return 12;
+    case 49: return 13;
+    case 47: return 11;
+    case 57: return 12;
+    default: break;
+    }
+  }
   return TileCfg<F>::TILE_LOG;
 }
 
@@ -528,6 +538,16 @@ int launch_tile_pass(const uint32_t* src, uint32_t* dst, const PassParams& p, in
     case 28: return launch_tile_pass_geom<F, 2, 8>(src, dst, p, S, s);
     case 29: return launch_tile_pass_geom<F, 2, 9>(src, dst, p, S, s);
     case 37: return launch_tile_pass_geom<F, 3, 7>(src, dst, p, S, s);
+    default: break;
+    }
+  }
+  if constexpr (F::N == 1) {
+    switch (tile_geom_override()) {
+    case 58: return launch_tile_pass_geom<F, 5, 8>(src, dst, p, S, s);
+    case 48: return launch_tile_pass_geom<F, 4, 8>(src, dst, p, S, s);
+    case 49: return launch_tile_pass_geom<F, 4, 9>(src, dst, p, S, s);
+    case 47: return launch_tile_pass_geom<F, 4, 7>(src, dst, p, S, s);
+    case 57: return launch_tile_pass_geom<F, 5, 7>(src, dst, p, S, s);
     default: break;
     }
   }
@@ -699,7 +719,7 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
                    total >= ((uint64_t)1 << tile_log_for<F>()) && F::N <= 12;
   if (const char* ev = getenv("B200_NTT_TILES")) use_tiles = use_tiles && atoi(ev) != 0;
   int radices[32];
-  const int npass = use_tiles ? plan_tile_passes(n_log, TileCfg<F>::MAX_S, radices) : plan_passes(n_log, maxr, radices);
+  const int npass = use_tiles ? plan_tile_passes(n_log, std::min(TileCfg<F>::MAX_S, tile_log_for<F>()), radices) : plan_passes(n_log, maxr, radices);
 
   PassParams p;
   memset(&p, 0, sizeof(p));
