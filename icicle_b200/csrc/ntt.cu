@@ -340,6 +340,62 @@ __device__ __forceinline__ void tile_round(F (&e)[1 << LOGE], const PassParams& 
   }
 }
 
+
+// kFourStep inter-pass twiddles for the Q-stage last round: the 2^Q elements of a group share the column index l and have
+// m = mh*2^Q + k, so rev_S(m) = rev_Q(k)*2^(S-Q) + rev_{S-Q}(mh) and the twiddle of element k is b0 * g^(rev_Q(k)) with
+// b0 = w_L^(l*rev_{S-Q}(mh)), g = w_L^(l*2^(S-Q)): two table look-ups per group, the rest by repeated multiplication.
+template <class F, int LOGE, int Q>
+__device__ __forceinline__ void tile_interpass(F (&e)[1 << LOGE], const PassParams& p, const uint32_t* eid, uint32_t logC, uint64_t col0, uint64_t rmask,
+                                               uint32_t S)
+{
+  constexpr int G = (1 << LOGE) >> Q;
+  const uint64_t dom_mask = (1ull << p.dom_log) - 1;
+  const uint32_t sh = p.dom_log - (p.lo + S);
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    const uint32_t m0 = eid[g << Q] >> logC, c = eid[g << Q] & ((1u << logC) - 1);
+    const uint64_t colg = col0 + c;
+    const uint64_t l = p.rot ? ((colg & rmask) >> p.done) : (colg & ((1ull << p.lo) - 1));
+    uint64_t ex0 = (l * (uint64_t)(__brev(m0) >> (32 - S))) << sh;
+    uint64_t exg = ((l << (S - Q)) << sh) & dom_mask;
+    if (p.inverse) {
+      ex0 = (0 - ex0) & dom_mask;
+      exg = (0 - exg) & dom_mask;
+    }
+    F t = load_twiddle<F>(p.tw, ex0 & dom_mask);
+    const F gs = load_twiddle<F>(p.tw, exg);
+    F pw[1 << Q];
+#pragma unroll
+    for (int j = 0; j < (1 << Q); j++) {
+      pw[j] = t;
+      if (j + 1 < (1 << Q)) t = t * gs;
+    }
+#pragma unroll
+    for (int k = 0; k < (1 << Q); k++) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      int rk = 0;
+#pragma unroll
+      for (int b = 0; b < Q; b++) rk |= ((k >> b) & 1) << (Q - 1 - b);
+      e[(g << Q) + k] = e[(g << Q) + k] * pw[rk];
+    }
+  }
+}
+
+template <class F, int LOGE, int Q>
+struct InterpassDispatch {
+  static __device__ __forceinline__ void run(int q, F (&e)[1 << LOGE], const PassParams& p, const uint32_t* eid, uint32_t logC, uint64_t col0,
+                                             uint64_t rmask, uint32_t S)
+  {
+    if (q == Q) tile_interpass<F, LOGE, Q>(e, p, eid, logC, col0, rmask, S);
+    else InterpassDispatch<F, LOGE, Q - 1>::run(q, e, p, eid, logC, col0, rmask, S);
+  }
+};
+template <class F, int LOGE>
+struct InterpassDispatch<F, LOGE, 0> {
+  static __device__ __forceinline__ void run(int, F (&)[1 << LOGE], const PassParams&, const uint32_t*, uint32_t, uint64_t, uint64_t, uint32_t) {}
+};
+
 template <class F, int LOGE, int Q>
 struct RoundDispatch {
   static __device__ __forceinline__ void run(int q, F (&e)[1 << LOGE], const PassParams& p, uint32_t a, const uint32_t* eid, uint32_t logC,
@@ -427,20 +483,16 @@ k_ntt_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassPar
     RoundDispatch<F, LOGE, LOGE>::run(q, e, p, (uint32_t)a, eid, logC, col0, rmask, twsm, S);
     // ---- store ----
     if (last_round) {
+      if constexpr (kFourStep) {
+        // inter-pass twiddle w_L^(l * rev_S(m)), L = 2^(lo+S), l = untransformed index below the digit (none in the last pass)
+        if (lo > 0) InterpassDispatch<F, LOGE, LOGE>::run(q, e, p, eid, logC, col0, rmask, S);
+      }
 #pragma unroll
       for (int u = 0; u < E; u++) {
         const uint32_t m = eid[u] >> logC, c = eid[u] & (C - 1);
         const uint64_t colg = col0 + c;
         if (colg >= total_cols) continue;
         uint64_t idx;
-        if constexpr (kFourStep) {
-          if (lo > 0) { // inter-pass twiddle w_L^(l * rev_S(m)), L = 2^(lo+S), l = untransformed index below the digit
-            const uint64_t l = p.rot ? ((colg & rmask) >> p.done) : (colg & ((1ull << lo) - 1));
-            uint64_t ex = (l * (uint64_t)(__brev(m) >> (32 - S))) << (p.dom_log - (lo + S));
-            if (p.inverse) ex = (0 - ex) & ((1ull << p.dom_log) - 1);
-            e[u] = e[u] * load_twiddle<F>(p.tw, ex);
-          }
-        }
         if (p.rot) {
           const uint64_t lowfull = colg & rmask;
           const uint64_t mrev = (uint64_t)(__brev(m) >> (32 - S));
