@@ -411,7 +411,7 @@ struct RoundDispatch<F, LOGE, 0> {
 };
 
 template <class F, int LOGE, int LOGT>
-__global__ void __launch_bounds__(1 << LOGT, (LOGT >= 9 ? 1 : (LOGT == 8 ? 2 : 4)))
+__global__ void __launch_bounds__(1 << LOGT, (LOGT >= 9 ? 1 : (LOGT == 8 ? 2 : (LOGT == 7 ? 4 : 8))))
 k_ntt_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassParams p, uint32_t S, uint64_t total_cols)
 {
   constexpr int E = 1 << LOGE;
@@ -576,6 +576,8 @@ int tile_log_for()
     case 49: return 13;
     case 47: return 11;
     case 57: return 12;
+    case 46: return 10;
+    case 56: return 11;
     default: break;
     }
   }
@@ -600,6 +602,8 @@ int launch_tile_pass(const uint32_t* src, uint32_t* dst, const PassParams& p, in
     case 49: return launch_tile_pass_geom<F, 4, 9>(src, dst, p, S, s);
     case 47: return launch_tile_pass_geom<F, 4, 7>(src, dst, p, S, s);
     case 57: return launch_tile_pass_geom<F, 5, 7>(src, dst, p, S, s);
+    case 46: return launch_tile_pass_geom<F, 4, 6>(src, dst, p, S, s);
+    case 56: return launch_tile_pass_geom<F, 5, 6>(src, dst, p, S, s);
     default: break;
     }
   }
@@ -771,7 +775,9 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
                    total >= ((uint64_t)1 << tile_log_for<F>()) && F::N <= 12;
   if (const char* ev = getenv("B200_NTT_TILES")) use_tiles = use_tiles && atoi(ev) != 0;
   int radices[32];
-  const int npass = use_tiles ? plan_tile_passes(n_log, std::min(TileCfg<F>::MAX_S, tile_log_for<F>()), radices) : plan_passes(n_log, maxr, radices);
+  int max_s = std::min(TileCfg<F>::MAX_S, tile_log_for<F>());
+  if (const char* ev = getenv("B200_NTT_MAXS")) max_s = std::max(5, std::min(atoi(ev), tile_log_for<F>()));
+  const int npass = use_tiles ? plan_tile_passes(n_log, max_s, radices) : plan_passes(n_log, maxr, radices);
 
   PassParams p;
   memset(&p, 0, sizeof(p));
