@@ -233,6 +233,12 @@ def msm_choose_c(curve, msm_size, config=None):
     return lib.b200_msm_choose_c(int(curve), int(msm_size), C.byref(c))
 
 
+def msm_pair_levels(curve, msm_size, c=0, config=None):
+    """Number of batched-affine pair levels the MSM schedule will run for this size (planning query)."""
+    cfg = (config or MSMConfig(c=c))._c()
+    return lib.b200_msm_pair_levels(int(curve), int(msm_size), C.byref(cfg))
+
+
 # ---- NTT --------------------------------------------------------------------------------------------------------------
 class NTTConfig:
     """icicle::NTTConfig<S> (icicle/include/icicle/ntt.h:52-64); defaults of default_ntt_config() (ntt.h:73-86)."""

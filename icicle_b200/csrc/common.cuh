@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include "../../include/icicle_b200.h"
 #include "ff.cuh"
 #include "ext.cuh"
@@ -41,6 +42,14 @@ struct Scratch {
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
       uint64_t thresh = UINT64_MAX;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    // The MSM gathers 32/64-byte points at random; with the default L2 fetch granularity every gather pulls a whole 128-byte
+    // line from HBM (measured with ncu: 2x the algorithmic bytes).  Ask for sector-granular fills; streaming kernels
+    // request whole lines anyway and are unaffected.
+    {
+      size_t gran = 32;
+      if (const char* ev = getenv("B200_L2_FETCH")) gran = (size_t)atoi(ev);
+      if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
     }
     configured_mask |= (1ull << dev);
   }

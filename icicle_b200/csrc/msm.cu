@@ -7,6 +7,7 @@
   extern "C" int b200_msm_entry_##ID(const void*, const void*, int, const b200_msm_config*, void*) __attribute__((weak)); \
   extern "C" int b200_msm_precompute_entry_##ID(const void*, int, const b200_msm_config*, void*) __attribute__((weak)); \
   extern "C" int b200_msm_plan_c_entry_##ID(int, const b200_msm_config*) __attribute__((weak));                         \
+  extern "C" int b200_msm_plan_levels_entry_##ID(int, const b200_msm_config*) __attribute__((weak));                    \
   extern "C" int b200_ec_sum_entry_##ID(const void*, int, const b200_vec_ops_config*, void*) __attribute__((weak));
 DECL(0) DECL(1) DECL(2) DECL(3) DECL(4) DECL(5) DECL(6) DECL(8)
 
@@ -70,6 +71,14 @@ __attribute__((visibility("default"))) int b200_msm_choose_c(int curve, int msm_
 {
   if (!cfg) return -1;
 #define CALL(TU) return b200_msm_plan_c_entry_##TU(msm_size, cfg)
+  ALL_CASES(CALL)
+#undef CALL
+}
+
+__attribute__((visibility("default"))) int b200_msm_pair_levels(int curve, int msm_size, const b200_msm_config* cfg)
+{
+  if (!cfg) return -1;
+#define CALL(TU) return b200_msm_plan_levels_entry_##TU(msm_size, cfg)
   ALL_CASES(CALL)
 #undef CALL
 }

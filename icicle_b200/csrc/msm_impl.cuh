@@ -26,7 +26,9 @@
 // algorithmic HBM bytes are only |scalar| + |affine| per point (96 B for BN254 G1).
 #pragma once
 #include "common.cuh"
+#include "msm_pairs.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
@@ -125,19 +127,24 @@ __global__ void __launch_bounds__(256) k_digits(
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr uint32_t P_EMPTY = 0xffffffffu;
 
-template <class F>
+// DIRECT = false: entries are the radix-sorted (key, point index | sign) pairs, points gathered from `points`.
+// DIRECT = true : entries are the affine points of a pair-tree level (msm_pairs.cuh): point e = points[e], no sign, no
+//                 sentinel, and the live entry count is read from device memory (*n_dev) because it is only known there.
+template <class F, bool DIRECT>
 __global__ void __launch_bounds__(MSM_THREADS) k_accumulate(
-  const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n_entries, uint32_t slice, uint32_t sentinel,
-  const uint32_t* __restrict__ points, uint32_t* __restrict__ buckets, uint32_t* __restrict__ pkey, uint32_t* __restrict__ pflag,
-  uint32_t* __restrict__ ppt, uint64_t n_slices)
+  const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n_entries, const uint32_t* __restrict__ n_dev, uint32_t slice,
+  uint32_t sentinel, const uint32_t* __restrict__ points, uint32_t* __restrict__ buckets, uint32_t* __restrict__ pkey,
+  uint32_t* __restrict__ pflag, uint32_t* __restrict__ ppt, uint64_t n_slices)
 {
   constexpr int AW = 2 * F::N, XW = 4 * F::N;
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_slices) return;
+  if (DIRECT) n_entries = *n_dev;
   const uint64_t beg = t * slice;
   const uint64_t end = (beg + slice < n_entries) ? beg + slice : n_entries;
   pkey[2 * t] = P_EMPTY;
   pkey[2 * t + 1] = P_EMPTY;
+  if (beg >= n_entries) return;
 
   uint32_t cur = keys[beg];
   if (cur == sentinel) return;
@@ -145,9 +152,9 @@ __global__ void __launch_bounds__(MSM_THREADS) k_accumulate(
   int slot = 0; // head partial goes to slot 0, tail partial to slot 1
   XYZZ<F> acc = XYZZ<F>::inf();
 
-  uint32_t v = vals[beg];
+  uint32_t v = DIRECT ? (uint32_t)beg : vals[beg];
   Affine<F> nxt = load_affine<F>(points + (uint64_t)(v & ~SIGN_BIT) * AW);
-  bool nxt_neg = (v & SIGN_BIT) != 0;
+  bool nxt_neg = !DIRECT && (v & SIGN_BIT) != 0;
 
   for (uint64_t e = beg; e < end; e++) {
     Affine<F> p = nxt;
@@ -155,9 +162,9 @@ __global__ void __launch_bounds__(MSM_THREADS) k_accumulate(
     uint32_t knext = sentinel;
     if (e + 1 < n_entries) knext = keys[e + 1];
     if (e + 1 < end && knext != sentinel) {
-      uint32_t v2 = vals[e + 1];
+      uint32_t v2 = DIRECT ? (uint32_t)(e + 1) : vals[e + 1];
       nxt = load_affine<F>(points + (uint64_t)(v2 & ~SIGN_BIT) * AW);
-      nxt_neg = (v2 & SIGN_BIT) != 0;
+      nxt_neg = !DIRECT && (v2 & SIGN_BIT) != 0;
     }
     if (neg) p.y = p.y.neg();
     acc.add_affine(p);
@@ -341,53 +348,6 @@ __global__ void __launch_bounds__(256) k_to_mont(const uint32_t* __restrict__ in
     store_fp<B>(out + i * B::N, load_fp<B>(in + i * B::N).to_mont());
 }
 
-template <class F>
-struct base_fp {
-  typedef F type;
-};
-template <class P>
-struct base_fp<Fp2<P>> {
-  typedef Fp<P> type;
-};
-
-// Fermat inversion in the base field / its quadratic extension (set-up / precompute only)
-template <class P>
-__device__ Fp<P> inv_fp(const Fp<P>& a)
-{
-  typedef Fp<P> B;
-  uint32_t e[B::N];
-#pragma unroll
-  for (int i = 0; i < B::N; i++) e[i] = P::p(i);
-  { // e = p - 2 with borrow propagation (several moduli end in ...00000001)
-    uint32_t borrow = 2;
-    for (int i = 0; i < (int)(sizeof(e) / sizeof(e[0])) && borrow; i++) {
-      uint32_t before = e[i];
-      e[i] = before - borrow;
-      borrow = (before < borrow) ? 1u : 0u;
-    }
-  }
-  B r = B::one();
-  for (int i = B::N * 32 - 1; i >= 0; i--) {
-    r = r * r;
-    if ((e[i / 32] >> (i % 32)) & 1) r = r * a;
-  }
-  return r;
-}
-template <class P>
-__device__ Fp<P> inv_el(const Fp<P>& a)
-{
-  return inv_fp(a);
-}
-template <class P>
-__device__ Fp2<P> inv_el(const Fp2<P>& a)
-{
-  // 1/(a0 + a1 u) = (a0 - a1 u) / (a0^2 - nr a1^2)
-  typedef Fp<P> B;
-  B n = B::sqr(a.c0) - Fp2<P>::mul_nr(B::sqr(a.c1));
-  B ni = inv_fp(n);
-  return {a.c0 * ni, (a.c1 * ni).neg()};
-}
-
 // precompute: out[pf*i + j] = 2^(j*shift) * in[i] (affine).  Thread per input point.
 template <class F>
 __global__ void __launch_bounds__(MSM_THREADS) k_precompute(
@@ -469,6 +429,34 @@ MsmPlan make_plan(int msm_size, const b200_msm_config* cfg)
   return pl;
 }
 
+// number of MSMs of a batch processed together (entry counts must fit 31 bits and memory stays bounded)
+inline int batch_chunk(uint32_t n, const MsmPlan& pl, int batch, bool shared, const b200_msm_config* cfg)
+{
+  const uint64_t ent_per_msm = (uint64_t)n * pl.nwin;
+  const uint64_t max_entries = 1ull << 30;
+  int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)batch, max_entries / std::max<uint64_t>(ent_per_msm, 1)));
+  if (cfg->ext_nof_chunks > 0) chunk = std::max(1, (batch + cfg->ext_nof_chunks - 1) / cfg->ext_nof_chunks);
+  if (!shared) { // point indices must fit 31 bits
+    while (chunk > 1 && (uint64_t)chunk * n * pl.pf >= (1ull << 31)) chunk--;
+  }
+  return chunk;
+}
+
+// Number of batched-affine pair levels (msm_pairs.cuh) run before the XYZZ accumulation.  L levels halve the sorted list L
+// times with ~6-product affine adds instead of 10-product mixed adds.  Measured on B200 (profiles/r1_msm_pair_levels.txt):
+// each level costs ~0.7 ms of small inversion-tree kernels on top of its per-pair work, so the levels pay off from ~2^26
+// entries, and the deeper levels are worth it while the bucket runs stay >= 8 entries long.
+inline int choose_pair_levels(uint64_t max_ent, uint64_t max_buckets)
+{
+  int levels = 0;
+  const double avg_run = (double)max_ent / (double)std::max<uint64_t>(max_buckets, 1);
+  if (max_ent >= (1ull << 26) && avg_run >= 8.0) {
+    while ((8 << levels) <= avg_run && levels < 5) levels++;
+  }
+  if (const char* ev = getenv("B200_MSM_PAIR_LEVELS")) levels = std::max(0, std::min(8, atoi(ev)));
+  return levels;
+}
+
 // Device-resident core: scalars (standard or Montgomery form), points already in Montgomery form, results written to d_res
 // (device).  Everything is enqueued on `s`; nothing here synchronises.
 template <class C>
@@ -481,13 +469,7 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
   int err;
   // ---- batch chunking so that entry counts fit 31 bits and memory stays bounded ----------------------------------------
   const uint64_t ent_per_msm = (uint64_t)n * pl.nwin;
-  uint64_t max_entries = 1ull << 30;
-  int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)batch, max_entries / std::max<uint64_t>(ent_per_msm, 1)));
-  if (cfg->ext_nof_chunks > 0) chunk = std::max(1, (batch + cfg->ext_nof_chunks - 1) / cfg->ext_nof_chunks);
-  // point indices must fit 31 bits
-  if (!shared) {
-    while (chunk > 1 && (uint64_t)chunk * n * pl.pf >= (1ull << 31)) chunk--;
-  }
+  int chunk = batch_chunk(n, pl, batch, shared, cfg);
   if ((uint64_t)n * pl.pf >= (1ull << 31) || ent_per_msm >= (1ull << 32)) return B200_INVALID_ARGUMENT;
 
   const uint64_t max_ent = ent_per_msm * chunk;
@@ -527,6 +509,52 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
   if ((err = s_red0.alloc(std::max<uint64_t>(max_chunks, 1) * XW * 4, s))) return err;
   if ((err = s_red1.alloc(std::max<uint64_t>(max_chunks / 2 + 1, 1) * XW * 4, s))) return err;
 
+  // ---- batched-affine pair levels (msm_pairs.cuh) ---------------------------------------------------------------------
+  int levels = choose_pair_levels(max_ent, max_buckets);
+  constexpr uint32_t PAIR_J = 32, INV_G = 64;
+  const uint32_t nb_max = (uint32_t)max_buckets;
+  uint64_t cap[10];
+  cap[0] = max_ent;
+  for (int l = 0; l < levels; l++) cap[l + 1] = cap[l] / 2 + nb_max + 1;
+  Scratch s_off[2], s_cnt, s_scan, s_lvl[2], s_lkey[2], s_pbuf, s_tree, s_tpre;
+  size_t scan_bytes = 0;
+  uint64_t tree_m[8];
+  int tree_levels = 0;
+  uint64_t tree_total = 0;
+  if (levels > 0) {
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(nb_max + 1), s);
+    uint64_t cap_max = cap[0]; // sparse lists (few entries, many buckets) have a growing upper bound
+    for (int l = 1; l < levels; l++) cap_max = std::max(cap_max, cap[l]);
+    uint64_t m = (((cap_max + 1) / 2 + (uint64_t)PAIR_J * PAIR_THREADS - 1) / ((uint64_t)PAIR_J * PAIR_THREADS)) * PAIR_THREADS;
+    for (;;) {
+      tree_m[tree_levels++] = m;
+      tree_total += m;
+      if (m <= INV_G) break;
+      m = (m + INV_G - 1) / INV_G;
+    }
+    bool ok = true;
+    for (int b = 0; b < 2 && ok; b++) {
+      ok = ok && !s_off[b].alloc(((size_t)nb_max + 1) * 4, s);
+      if (b < levels) {
+        ok = ok && !s_lvl[b].alloc((size_t)cap[b + 1] * AW * 4, s);
+        ok = ok && !s_lkey[b].alloc((size_t)cap[b + 1] * 4, s);
+      }
+    }
+    ok = ok && !s_cnt.alloc(((size_t)nb_max + 1) * 4, s) && !s_scan.alloc(scan_bytes, s) &&
+         !s_pbuf.alloc(((size_t)cap[0] / 2 + 1) * F::BYTES, s) && !s_tree.alloc((size_t)tree_total * F::BYTES, s) &&
+         !s_tpre.alloc((size_t)tree_total * F::BYTES, s);
+    if (!ok) { // not enough memory for the level buffers: fall back to the XYZZ-only schedule
+      levels = 0;
+      for (int b = 0; b < 2; b++) { s_off[b].release(); s_lvl[b].release(); s_lkey[b].release(); }
+      s_cnt.release(); s_scan.release(); s_pbuf.release(); s_tree.release(); s_tpre.release();
+    }
+  }
+  if (levels > 0) {
+    uint32_t sl = (uint32_t)std::min<uint64_t>(128, std::max<uint64_t>(8, cap[levels] / target_threads));
+    while ((cap[levels] + sl - 1) / sl > max_slices) sl++; // the partial-slot buffers were sized for max_slices
+    slice = sl;
+  }
+
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int bl = std::min(chunk, batch - b0);
     const uint64_t n_ent = ent_per_msm * bl;
@@ -553,11 +581,86 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
     prof.mark("sort");
     // K8
     B200_CUDA_TRY(cudaMemsetAsync(s_bkt.p, 0, n_buckets * XW * 4, s), B200_UNKNOWN_ERROR);
-    const uint64_t n_slices = (n_ent + slice - 1) / slice;
-    k_accumulate<F><<<(unsigned)((n_slices + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
-      dk.Current(), dv.Current(), n_ent, slice, sentinel, pts, s_bkt.as<uint32_t>(), s_pkey.as<uint32_t>(), s_pflag.as<uint32_t>(),
-      s_ppt.as<uint32_t>(), n_slices); B200_LAUNCHED(1);
-    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    uint64_t n_slices;
+    if (levels == 0) {
+      n_slices = (n_ent + slice - 1) / slice;
+      k_accumulate<F, false><<<(unsigned)((n_slices + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
+        dk.Current(), dv.Current(), n_ent, nullptr, slice, sentinel, pts, s_bkt.as<uint32_t>(), s_pkey.as<uint32_t>(),
+        s_pflag.as<uint32_t>(), s_ppt.as<uint32_t>(), n_slices); B200_LAUNCHED(1);
+      B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    } else {
+      const uint32_t nb = (uint32_t)n_buckets;
+      const unsigned gb = (nb + 1 + 255) / 256;
+      k_bounds<<<gb, 256, 0, s>>>(dk.Current(), (uint32_t)n_ent, nb, s_off[0].as<uint32_t>()); B200_LAUNCHED(1);
+      uint64_t capl = n_ent; // upper bound of the current level's length (the exact length lives in off[nb] on the device)
+      const uint32_t *lk = dk.Current(), *lp = pts;
+      uint64_t lcap = 0;     // plane stride of the current (planar) level buffer
+      uint4* pbuf = s_pbuf.as<uint4>();
+      const uint64_t pcap = cap[0] / 2 + 1;
+      for (int l = 0; l < levels; l++) {
+        uint32_t* off_c = s_off[l & 1].as<uint32_t>();
+        uint32_t* off_n = s_off[(l + 1) & 1].as<uint32_t>();
+        k_pair_counts<<<gb, 256, 0, s>>>(off_c, nb, s_cnt.as<uint32_t>()); B200_LAUNCHED(1);
+        B200_CUDA_TRY(cub::DeviceScan::ExclusiveSum(s_scan.p, scan_bytes, s_cnt.as<uint32_t>(), off_n, (int)(nb + 1), s), B200_UNKNOWN_ERROR);
+        const uint64_t nq = (capl + 1) / 2;
+        const unsigned gp = (unsigned)((nq + (uint64_t)PAIR_J * PAIR_THREADS - 1) / ((uint64_t)PAIR_J * PAIR_THREADS));
+        const uint32_t nthr = gp * PAIR_THREADS;
+        uint32_t* tree = s_tree.as<uint32_t>();
+        uint32_t* tpre = s_tpre.as<uint32_t>();
+        uint32_t* out_p = s_lvl[l & 1].as<uint32_t>();
+        uint32_t* out_k = s_lkey[l & 1].as<uint32_t>();
+        const uint64_t ocap = cap[(l & 1) + 1];
+        const bool last = (l + 1 == levels);
+        if (l == 0) {
+          PairSrc<F, true> src = {lk, dv.Current(), lp, 0};
+          k_pair_prefix<F, true><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, nb, PAIR_J, pbuf, pcap, tree);
+        } else {
+          PairSrc<F, false> src = {lk, nullptr, lp, lcap};
+          k_pair_prefix<F, false><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, nb, PAIR_J, pbuf, pcap, tree);
+        }
+        B200_LAUNCHED(1);
+        // batch inversion of the nthr per-thread totals (in place in tree[0 .. nthr))
+        {
+          uint64_t m[8], o[8];
+          int R = 0;
+          uint64_t mm = nthr, oo = 0;
+          for (;;) {
+            m[R] = mm; o[R] = oo; R++;
+            if (mm <= INV_G) break;
+            oo += mm;
+            mm = (mm + INV_G - 1) / INV_G;
+          }
+          for (int r = 0; r + 1 < R; r++) {
+            k_inv_up<F><<<(unsigned)((m[r + 1] + 127) / 128), 128, 0, s>>>(
+              tree + o[r] * F::N, (uint32_t)m[r], INV_G, tpre + o[r] * F::N, tree + o[r + 1] * F::N, (uint32_t)m[r + 1]); B200_LAUNCHED(1);
+          }
+          k_inv_top<F><<<1, 32, 0, s>>>(tree + o[R - 1] * F::N, (uint32_t)m[R - 1], tpre + o[R - 1] * F::N); B200_LAUNCHED(1);
+          for (int r = R - 2; r >= 0; r--) {
+            k_inv_down<F><<<(unsigned)((m[r + 1] + 127) / 128), 128, 0, s>>>(
+              tree + o[r] * F::N, (uint32_t)m[r], INV_G, tpre + o[r] * F::N, tree + o[r + 1] * F::N, (uint32_t)m[r + 1]); B200_LAUNCHED(1);
+          }
+        }
+        if (l == 0) {
+          PairSrc<F, true> src = {lk, dv.Current(), lp, 0};
+          if (last) k_pair_apply<F, true, false><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, off_n, nb, PAIR_J, pbuf, pcap, tree, out_p, ocap, out_k);
+          else k_pair_apply<F, true, true><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, off_n, nb, PAIR_J, pbuf, pcap, tree, out_p, ocap, out_k);
+        } else {
+          PairSrc<F, false> src = {lk, nullptr, lp, lcap};
+          if (last) k_pair_apply<F, false, false><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, off_n, nb, PAIR_J, pbuf, pcap, tree, out_p, ocap, out_k);
+          else k_pair_apply<F, false, true><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, off_n, nb, PAIR_J, pbuf, pcap, tree, out_p, ocap, out_k);
+        }
+        B200_LAUNCHED(1);
+        B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+        lk = out_k; lp = out_p; lcap = ocap;
+        capl = capl / 2 + nb + 1;
+      }
+      prof.mark("pair_levels");
+      n_slices = (capl + slice - 1) / slice;
+      k_accumulate<F, true><<<(unsigned)((n_slices + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
+        lk, nullptr, 0, s_off[levels & 1].as<uint32_t>() + nb, slice, 0xffffffffu, lp, s_bkt.as<uint32_t>(), s_pkey.as<uint32_t>(),
+        s_pflag.as<uint32_t>(), s_ppt.as<uint32_t>(), n_slices); B200_LAUNCHED(1);
+      B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    }
     prof.mark("accumulate");
     {
       // hierarchical stitch of the boundary partials (see k_reduce_partials), then a final owner walk over <= 512 slots

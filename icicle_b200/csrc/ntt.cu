@@ -523,6 +523,8 @@ k_ntt_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassPar
   }
 }
 
+#include "ntt31.cuh"
+
 // tile geometry per field width: elements per thread (2^LOGE) and threads per CTA (2^LOGT)
 template <class F>
 struct TileCfg {
@@ -777,6 +779,12 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
   int radices[32];
   int max_s = std::min(TileCfg<F>::MAX_S, tile_log_for<F>());
   if (const char* ev = getenv("B200_NTT_MAXS")) max_s = std::max(5, std::min(atoi(ev), tile_log_for<F>()));
+  // 4-byte fields, natural order in and out: dedicated 32-column tile pass (ntt31.cuh), 5..9 stages per pass
+  bool fast31 = false;
+  if constexpr (F::N == 1) {
+    fast31 = use_tiles && scatter_out && !gather_in && n_log >= 10 && !getenv("B200_NTT31_OFF");
+    if (fast31) max_s = 9;
+  }
   const int npass = use_tiles ? plan_tile_passes(n_log, max_s, radices) : plan_passes(n_log, maxr, radices);
 
   PassParams p;
@@ -823,7 +831,11 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
       p.out_mul = p.last ? out_mul : nullptr;
       p.out_scale = p.last ? out_scale : nullptr;
       uint32_t* dstp = p.last ? (uint32_t*)dout : ((i % 2 == 0) ? stmp.as<uint32_t>() : stmpB.as<uint32_t>());
-      if ((err = launch_tile_pass<F>(src, dstp, p, r, s))) return err;
+      if (fast31) {
+        if ((err = launch_ntt31<F>(src, dstp, p, r, s))) return err;
+      } else if ((err = launch_tile_pass<F>(src, dstp, p, r, s))) {
+        return err;
+      }
       prof.mark("pass");
       src = dstp;
       done += r;

@@ -1,0 +1,239 @@
+// Shared-memory tile pass for the 4-byte (31-bit) NTT fields: BabyBear, KoalaBear.  Included by ntt.cu (needs PassParams
+// and load_twiddle from there).
+//
+// These are the one family where the transform is genuinely HBM-sized work (8 B of traffic per element and pass against
+// ~80 instructions), so the pass is organised around memory behaviour rather than around the register file:
+//   * one CTA (256 threads) owns a tile of 2^S strided rows x 32 contiguous columns, i.e. every global access of a warp is
+//     one full 128-byte line (B200 fills L2 with whole lines even for a single 32-byte sector, so narrower row segments would
+//     multiply the read traffic); a 2^S x 33-word padded tile keeps both row-wise and column-wise shared-memory accesses
+//     bank-conflict free;
+//   * ~68 KB of shared memory and <= 64 registers per thread leave three CTAs per SM, so one CTA's loads, another's
+//     butterflies and a third's stores overlap (the generic tile kernel runs one 512-thread CTA per SM for these fields);
+//   * the sub-transform is a pure 2^S-point decimation-in-time NTT on rows stored bit-reversed at load time (free: it is
+//     only an address), radix-8 rounds with the lane = column, so every twiddle of a round is warp-uniform and comes from a
+//     2^(S-1)-entry table in shared memory; the column-dependent "four-step" factor w_L^(l*k) is applied once per element in
+//     the last round, by power iteration per lane (one table look-up per lane and pass);
+//   * the pass writes in the autosort layout of ntt.cu (digit written in natural frequency order just above the digits
+//     transformed so far), choosing lane = frequency for the first pass and lane = column afterwards so that stores are
+//     128-byte runs too.  Natural-order input and output (kNN), any batch, coset and inverse scaling folded in.
+// Reference semantics: icicle/backend/cpu/include/ntt_cpu.h:69-232 (see ntt.cu header); results are canonical field
+// elements, hence bit-identical to the reference whatever the schedule.
+#pragma once
+// (included inside ntt.cu's anonymous namespace, after PassParams / load_twiddle)
+
+constexpr int NTT31_THREADS = 256;
+constexpr int NTT31_ROWPAD = 33;
+
+template <class F, int Q>
+__device__ __forceinline__ void ntt31_dit_group(F (&e)[8], uint32_t a, uint32_t blow, const uint32_t* __restrict__ twsm, uint32_t S)
+{
+  // Q decimation-in-time stages t = a .. a+Q-1 on the 2^Q rows base + (j << a); blow = base mod 2^a.
+  // stage t pairs rows differing in bit t with twiddle w_{2^(t+1)}^(row mod 2^t) = twsm[(row mod 2^t) << (S-1-t)]
+#pragma unroll
+  for (int i = 0; i < Q; i++) {
+    const uint32_t t = a + i;
+#pragma unroll
+    for (int jj = 0; jj < (1 << i); jj++) {
+      F w;
+      w.v[0] = twsm[(blow + ((uint32_t)jj << a)) << (S - 1 - t)];
+#pragma unroll
+      for (int up = 0; up < (1 << (Q - 1 - i)); up++) {
+        const int j0 = (up << (i + 1)) | jj, j1 = j0 | (1 << i);
+        const F u = e[j0], v = e[j1] * w;
+        e[j0] = u + v;
+        e[j1] = u - v;
+      }
+    }
+  }
+}
+
+template <class F>
+__device__ __forceinline__ F ntt31_pow(F b, uint32_t ex)
+{
+  F r = F::one();
+  while (ex) {
+    if (ex & 1u) r = r * b;
+    b = b * b;
+    ex >>= 1;
+  }
+  return r;
+}
+
+// One round of Q stages over the whole tile.  LAST: apply the inter-pass twiddle (per lane l, per row k) before storing.
+template <class F, int Q, bool LAST>
+__device__ __forceinline__ void ntt31_round(uint32_t* __restrict__ tile, const uint32_t* __restrict__ twsm, uint32_t S, uint32_t a, uint32_t lane,
+                                            uint32_t warp, bool interpass, F g1)
+{
+  constexpr int NW = NTT31_THREADS / 32;
+  const uint32_t ngroups = 1u << (S - Q);
+  // LAST (a == S - Q): group g has base g; row k = g + (j << a) gets g1^k = T_g * G^j with G = g1^(2^a), T_g = g1^g
+  F G = F::one(), T = F::one(), g8 = F::one();
+  if (LAST && interpass) {
+    G = g1;
+    for (uint32_t i = 0; i < a; i++) G = G * G;
+    T = ntt31_pow(g1, warp);
+    g8 = ntt31_pow(g1, NW);
+  }
+  for (uint32_t g = warp; g < ngroups; g += NW) {
+    const uint32_t blow = g & ((1u << a) - 1);
+    const uint32_t base = ((g >> a) << (a + Q)) | blow;
+    F e[8];
+#pragma unroll
+    for (int j = 0; j < (1 << Q); j++) e[j].v[0] = tile[(base + ((uint32_t)j << a)) * NTT31_ROWPAD + lane];
+    ntt31_dit_group<F, Q>(e, a, blow, twsm, S);
+    if (LAST && interpass) {
+      F t = T;
+#pragma unroll
+      for (int j = 0; j < (1 << Q); j++) {
+        e[j] = e[j] * t;
+        if (j + 1 < (1 << Q)) t = t * G;
+      }
+      T = T * g8;
+    }
+#pragma unroll
+    for (int j = 0; j < (1 << Q); j++) tile[(base + ((uint32_t)j << a)) * NTT31_ROWPAD + lane] = e[j].v[0];
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassParams p, uint32_t S)
+{
+  static_assert(F::N == 1, "k_ntt31 is the 4-byte-field pass");
+  extern __shared__ uint32_t sm[];
+  uint32_t* tile = sm;
+  uint32_t* twsm = sm + ((size_t)NTT31_ROWPAD << S);
+  constexpr int NW = NTT31_THREADS / 32;
+  const uint32_t T = threadIdx.x, lane = T & 31, warp = T >> 5;
+  const uint32_t n_log = p.n_log;
+  const uint32_t rsh = n_log - S;           // the digit transformed by a pass sits in the top S bits of the position
+  const uint64_t rmask = (1ull << rsh) - 1; // everything below it: [untransformed (lo bits)][transformed so far (done bits)]
+  const uint64_t ntt_mask = (1ull << n_log) - 1;
+  const uint64_t dom_mask = (1ull << p.dom_log) - 1;
+  const uint64_t col0 = (uint64_t)blockIdx.x * 32;
+  const uint64_t colg = col0 + lane;
+  const uint64_t hi_part = (colg >> rsh) << n_log; // batch index (the tile never straddles two transforms: rsh >= 5)
+  const uint64_t lowfull = colg & rmask;
+
+  // ---- twiddle table of the 2^S-point sub-transform ----
+  for (uint32_t j = T; j < (1u << (S - 1)); j += NTT31_THREADS) {
+    uint64_t ex = (uint64_t)j << (p.dom_log - S);
+    if (p.inverse) ex = (0 - ex) & dom_mask;
+    twsm[j] = load_twiddle<F>(p.tw, ex).v[0];
+  }
+  // ---- load: row m of the tile goes to shared-memory row rev_S(m) ----
+  {
+    const uint32_t nrows = 1u << S;
+    constexpr int LD = 8; // independent 128-byte row loads in flight per warp
+    for (uint32_t m0 = warp; m0 < nrows; m0 += NW * LD) {
+      uint32_t v[LD];
+#pragma unroll
+      for (int u = 0; u < LD; u++) {
+        const uint32_t m = m0 + u * NW;
+        const uint64_t pos = hi_part | ((uint64_t)m << rsh) | lowfull;
+        v[u] = (m < nrows) ? src[pos] : 0u;
+      }
+      if (p.in_mul) {
+#pragma unroll
+        for (int u = 0; u < LD; u++) {
+          const uint32_t m = m0 + u * NW;
+          if (m < nrows) {
+            const uint64_t pin = (((uint64_t)m << rsh) | lowfull) & ntt_mask;
+            F x, c;
+            x.v[0] = v[u];
+            c.v[0] = p.in_mul[pin];
+            v[u] = (x * c).v[0];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < LD; u++) {
+        const uint32_t m = m0 + u * NW;
+        if (m < nrows) tile[(__brev(m) >> (32 - S)) * NTT31_ROWPAD + lane] = v[u];
+      }
+    }
+  }
+  // inter-pass factor of this lane: g1 = w_L^l, L = 2^(lo+S), l = untransformed index below the digit
+  const bool interpass = (p.lo > 0);
+  F g1 = F::one();
+  if (interpass) {
+    const uint64_t l = lowfull >> p.done;
+    uint64_t ex = (l << (p.dom_log - (p.lo + S))) & dom_mask;
+    if (p.inverse) ex = (0 - ex) & dom_mask;
+    g1 = load_twiddle<F>(p.tw, ex);
+  }
+  __syncthreads();
+
+  // ---- rounds of <= 3 DIT stages ----
+  uint32_t a = 0;
+  while (a < S) {
+    const uint32_t q = (S - a >= 3) ? 3 : (S - a);
+    const bool last = (a + q == S);
+    if (last) {
+      if (q == 3) ntt31_round<F, 3, true>(tile, twsm, S, a, lane, warp, interpass, g1);
+      else if (q == 2) ntt31_round<F, 2, true>(tile, twsm, S, a, lane, warp, interpass, g1);
+      else ntt31_round<F, 1, true>(tile, twsm, S, a, lane, warp, interpass, g1);
+    } else {
+      ntt31_round<F, 3, false>(tile, twsm, S, a, lane, warp, false, g1);
+    }
+    a += q;
+    __syncthreads();
+  }
+
+  // ---- store in the autosort layout: idx = batch | (untransformed << (S+done)) | (k << done) | (transformed so far) ----
+  const uint32_t done = p.done;
+  const uint32_t nrows = 1u << S;
+  if (done == 0) {
+    // first pass: each column is a contiguous run of 2^S frequencies -> lane = frequency
+    for (uint32_t task = warp; task < 32u * (nrows >> 5); task += NW) {
+      const uint32_t c = task & 31, k = ((task >> 5) << 5) | lane;
+      const uint64_t colc = col0 + c;
+      const uint64_t lf = colc & rmask;
+      const uint64_t idx = ((colc >> rsh) << n_log) | (lf << S) | k;
+      uint32_t v = tile[k * NTT31_ROWPAD + c];
+      if (p.last) {
+        const uint64_t kidx = idx & ntt_mask;
+        F x, m;
+        x.v[0] = v;
+        if (p.out_mul) { m.v[0] = p.out_mul[kidx]; v = (x * m).v[0]; }
+        else if (p.out_scale) { m.v[0] = p.out_scale[0]; v = (x * m).v[0]; }
+      }
+      dst[idx] = v;
+    }
+  } else {
+    // later passes (done >= 5): the 32 columns of a row stay adjacent -> lane = column
+    const uint64_t lo_done = lowfull & ((1ull << done) - 1);
+    const uint64_t up = (lowfull >> done) << (S + done);
+    F scale = F::one();
+    const bool has_scale = p.last && !p.out_mul && p.out_scale;
+    if (has_scale) scale.v[0] = p.out_scale[0];
+    for (uint32_t k = warp; k < nrows; k += NW) {
+      const uint64_t idx = hi_part | up | ((uint64_t)k << done) | lo_done;
+      uint32_t v = tile[k * NTT31_ROWPAD + lane];
+      if (p.last) {
+        F x, m;
+        x.v[0] = v;
+        if (p.out_mul) { m.v[0] = p.out_mul[idx & ntt_mask]; v = (x * m).v[0]; }
+        else if (has_scale) v = (x * scale).v[0];
+      }
+      dst[idx] = v;
+    }
+  }
+}
+
+template <class F>
+int launch_ntt31(const uint32_t* src, uint32_t* dst, const PassParams& p, int S, cudaStream_t s)
+{
+  if constexpr (F::N == 1) {
+    const uint64_t total = ((uint64_t)1 << p.n_log) * p.batch;
+    const uint64_t total_cols = total >> S;
+    const uint64_t blocks = total_cols / 32; // n_log - S >= 5: always a whole number of 32-column tiles
+    const size_t smem = (((size_t)NTT31_ROWPAD << S) + ((size_t)1 << (S - 1))) * 4;
+    B200_CUDA_TRY(cudaFuncSetAttribute(k_ntt31<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), B200_UNKNOWN_ERROR);
+    k_ntt31<F><<<(unsigned)blocks, NTT31_THREADS, smem, s>>>(src, dst, p, (uint32_t)S); B200_LAUNCHED(1);
+    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+    return B200_SUCCESS;
+  } else {
+    return B200_UNKNOWN_ERROR;
+  }
+}
+

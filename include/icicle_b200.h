@@ -137,6 +137,9 @@ B200_API int b200_msm(int curve, const void* scalars, const void* bases, int msm
 B200_API int b200_msm_precompute_bases(int curve, const void* input_bases, int nof_bases, const b200_msm_config* cfg, void* output_bases);
 /* window size b200_msm would pick for this problem (exposed for the bench sweep and for tests) */
 B200_API int b200_msm_choose_c(int curve, int msm_size, const b200_msm_config* cfg);
+/* number of batched-affine pair levels the MSM schedule runs before the XYZZ bucket accumulation (0 = XYZZ only); our own
+ * planning query, no reference counterpart (the reference has no such stage: cpu_msm.hpp:259-314 adds point by point) */
+B200_API int b200_msm_pair_levels(int curve, int msm_size, const b200_msm_config* cfg);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * NTT -- replaces NttImpl / NttInitDomainImpl / NttReleaseDomainImpl / NttGetRouFromDomainImpl

@@ -223,3 +223,113 @@ def test_pipelined_host_path_matches_device_path():
     dev = ib.msm(C, ib.to_device(s), ib.to_device(P), n)[0]       # device pointers -> single pass
     q = utils.field_params("bn254_fq")["p"]
     assert common.projective_to_affine_ints(host, 8, q) == common.projective_to_affine_ints(dev, 8, q)
+
+
+@pytest.fixture
+def pair_levels_env():
+    """B200_MSM_PAIR_LEVELS forces the number of batched-affine pair levels (msm_pairs.cuh) regardless of size."""
+    import os
+    old = os.environ.get("B200_MSM_PAIR_LEVELS")
+    yield lambda v: os.environ.__setitem__("B200_MSM_PAIR_LEVELS", str(v))
+    if old is None:
+        os.environ.pop("B200_MSM_PAIR_LEVELS", None)
+    else:
+        os.environ["B200_MSM_PAIR_LEVELS"] = old
+
+
+def test_bn254_pair_levels_vs_reference(ref, pair_levels_env):
+    """The batched-affine pair tree must give the same group element as the reference for every level count, including the
+    cases that need the special branches: the reference generator's 100 repeated points (doublings inside a bucket),
+    P + (-P), affine zero bases, bitsize=1 (one huge bucket), all-equal scalars, odd run lengths, tiny windows."""
+    C = ib.Curve.BN254_G1
+    rng = random.Random(11)
+    for n in (1, 2, 3, 100, (1 << 12) - 37, (1 << 14) + 5):
+        s = ref.generate_scalars(n)
+        P = ref.generate_affine_points(n)
+        exp = ref.msm(s, P, n)
+        for lv in (1, 2, 3, 5, 8):
+            pair_levels_env(lv)
+            for c in (0, 2, 7, 12):
+                got = ib.msm(C, s, P, n, ib.MSMConfig(c=c))
+                assert ref.projective_eq(got[0], exp[0]), (n, lv, c)
+    # distinct points, P and -P in the same bucket, zero bases, skewed scalars
+    n = 1 << 13
+    P = common.gen_g1_points("bn254", n, 78)
+    q = utils.field_params("bn254_fq")["p"]
+    Pn = P.copy()
+    yi = utils.from_limbs(P[:, 8:])
+    Pn[:, 8:] = utils.to_limbs([(q - y) % q for y in yi], 8)
+    P2 = np.concatenate([P[: n // 2], Pn[: n // 2]])          # second half = negatives of the first half
+    s = ref.generate_scalars(n)
+    s[n // 2:] = s[: n // 2]                                     # same scalars -> every bucket holds P and -P
+    P2[5::31] = 0
+    for Pt, st in ((P, s), (P2, s)):
+        exp = ref.msm(st, Pt, n)
+        for lv in (1, 3, 4):
+            pair_levels_env(lv)
+            for c in (0, 4, 9):
+                got = ib.msm(C, st, Pt, n, ib.MSMConfig(c=c))
+                if common.is_projective_zero(exp[0], 8):
+                    assert common.is_projective_zero(got[0], 8), (lv, c)
+                else:
+                    assert ref.projective_eq(got[0], exp[0]), (lv, c)
+    sc = [rng.choice((0, 1, 1, 1)) for _ in range(n)]
+    s1 = utils.to_limbs(sc, 8)
+    Pr = ref.generate_affine_points(n)
+    Pr[::17] = 0
+    exp = ref.msm(s1, Pr, n, bitsize=1)
+    big = utils.to_limbs([rng.randrange(1 << 253)] * n, 8)
+    exp_big = ref.msm(big, Pr, n)
+    for lv in (1, 4, 8):
+        pair_levels_env(lv)
+        got = ib.msm(C, s1, Pr, n, ib.MSMConfig(bitsize=1))
+        assert ref.projective_eq(got[0], exp[0]), lv
+        got = ib.msm(C, big, Pr, n)
+        assert ref.projective_eq(got[0], exp_big[0]), lv
+    # batch + precompute through the levels
+    nb_, batch = (1 << 10) + 3, 3
+    s = ref.generate_scalars(nb_ * batch)
+    P = ref.generate_affine_points(nb_ * batch)
+    exp = ref.msm(s, P, nb_, batch_size=batch, are_points_shared_in_batch=False)
+    pair_levels_env(2)
+    got = ib.msm(C, s, P, nb_, ib.MSMConfig(batch_size=batch, are_points_shared_in_batch=False, c=6))
+    for b in range(batch):
+        assert ref.projective_eq(got[b], exp[b]), b
+    pre = ib.msm_precompute_bases(C, P[:nb_], nb_, ib.MSMConfig(precompute_factor=3, c=7))
+    got = ib.msm(C, s, pre, nb_, ib.MSMConfig(precompute_factor=3, c=7, batch_size=batch, are_points_shared_in_batch=True))
+    exp = ref.msm(s, P[:nb_], nb_, batch_size=batch, are_points_shared_in_batch=True)
+    for b in range(batch):
+        assert ref.projective_eq(got[b], exp[b]), b
+
+
+def test_bn254_g2_pair_levels(ref, pair_levels_env):
+    C = ib.Curve.BN254_G2
+    n = 1 << 10
+    s = ref.generate_scalars(n)
+    P = ref.generate_affine_points(n, g2=True)
+    exp = ref.msm(s, P, n, g2=True)
+    for lv in (1, 3):
+        pair_levels_env(lv)
+        got = _skip_if_not_built(lambda: ib.msm(C, s, P, n, ib.MSMConfig(c=5)))
+        assert ref.projective_eq(got[0], exp[0], g2=True), lv
+
+
+def test_pair_levels_large_matches_xyzz_only(pair_levels_env):
+    """2^22 points: automatic schedule vs pair levels forced off / forced on (3 and 6 levels) -- same group element."""
+    C = ib.Curve.BN254_G1
+    n = 1 << 22
+    base = common.gen_g1_points("bn254", 1 << 10, 55)
+    dP = ib.to_device(np.tile(base, (n >> 10, 1)))
+    rs = np.random.RandomState(19)
+    s = rs.randint(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+    s[:, 7] &= 0x0FFFFFFF
+    ds = ib.to_device(s)
+    q = utils.field_params("bn254_fq")["p"]
+    auto = common.projective_to_affine_ints(ib.msm(C, ds, dP, n)[0], 8, q)
+    pair_levels_env(0)
+    plain = common.projective_to_affine_ints(ib.msm(C, ds, dP, n)[0], 8, q)
+    assert auto == plain
+    for lv in (3, 6):
+        pair_levels_env(lv)
+        deep = common.projective_to_affine_ints(ib.msm(C, ds, dP, n)[0], 8, q)
+        assert deep == plain, lv

@@ -9,6 +9,7 @@ import common
 
 logn = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 cs = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
+levels = sys.argv[3].split(",") if len(sys.argv) > 3 else [None]
 n = 1 << logn
 base = ib.to_device(common.gen_g1_points("bn254", 1 << 12, 1))
 P = base.repeat(n >> 12, 1).contiguous()
@@ -17,9 +18,11 @@ s[:, 7] = torch.randint(0, 0x30644E72, (n,), dtype=torch.int64, device="cuda").t
 s = s.contiguous()
 out = ib.device_empty(24).view(1, 24)
 ib.set_profiling(True)
-for c in cs:
+for c, lv in [(c, lv) for c in cs for lv in levels]:
+    if lv is not None:
+        os.environ["B200_MSM_PAIR_LEVELS"] = lv
     for rep in range(2):
         ib.msm(ib.Curve.BN254_G1, s, P, n, ib.MSMConfig(c=c, is_async=True), out)
     what, st = ib.last_profile()
     tot = sum(ms for _, ms in st)
-    print(f"msm 2^{logn} c={c or ib.msm_choose_c(ib.Curve.BN254_G1, n)}: total {tot:.3f} ms | " + " ".join(f"{k}={v:.3f}" for k, v in st), flush=True)
+    print(f"msm 2^{logn} levels={lv} c={c or ib.msm_choose_c(ib.Curve.BN254_G1, n)}: total {tot:.3f} ms | " + " ".join(f"{k}={v:.3f}" for k, v in st), flush=True)
