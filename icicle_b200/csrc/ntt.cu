@@ -782,8 +782,12 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
   // 4-byte fields, natural order in and out: dedicated 32-column tile pass (ntt31.cuh), 5..9 stages per pass
   bool fast31 = false;
   if constexpr (F::N == 1) {
-    fast31 = use_tiles && scatter_out && !gather_in && n_log >= 10 && !getenv("B200_NTT31_OFF");
-    if (fast31) max_s = 9;
+    fast31 = (cfg->ext_ntt_algorithm != B200_NTT_ALG_RADIX2) && !cfg->columns_batch && scatter_out && !gather_in && n_log >= 10 &&
+             !getenv("B200_NTT31_OFF");
+    if (fast31) {
+      max_s = 9;
+      use_tiles = true;
+    }
   }
   const int npass = use_tiles ? plan_tile_passes(n_log, max_s, radices) : plan_passes(n_log, maxr, radices);
 

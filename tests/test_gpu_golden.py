@@ -83,3 +83,28 @@ def test_ntt_and_vec_golden(name, field, fname):
     assert np.array_equal(ib.vector_add(field, a, b, 50), g["vec_add"].reshape(-1, L))
     assert np.array_equal(ib.vector_sub(field, a, b, 50), g["vec_sub"].reshape(-1, L))
     assert np.array_equal(ib.vector_mul(field, a, b, 50), g["vec_mul"].reshape(-1, L))
+
+
+@pytest.mark.parametrize("name,field", [("babybear", ib.Field.BABYBEAR), ("koalabear", ib.Field.KOALABEAR)])
+def test_small_field_ntt_big_golden(name, field):
+    """4-byte-field tile pass (csrc/ntt31.cuh) vs outputs of the unmodified reference CPU backend at 2^10 .. 2^18
+    (tests/golden/<field>_ntt_big.npz, tools/make_golden_smallfield.py): bit-exact, full arrays or SHA-256 of the bytes."""
+    import hashlib
+    g = np.load(os.path.join(GOLD, f"{name}_ntt_big.npz"))
+    p = utils.field_params(name)["p"]
+    ib.ntt_release_domain(field)
+    ib.ntt_init_domain(field, g["ntt_root"].reshape(-1))
+    cases = sorted({(int(k.split("_")[1][1:]), int(k.split("_")[2][1:])) for k in g.files if k.startswith("sha_")})
+    assert len(cases) == 9
+    for logn, batch in cases:
+        rs = np.random.RandomState(1000 + logn)
+        x = rs.randint(0, p, size=(batch << logn, 1), dtype=np.int64).astype(np.uint32)
+        for d in (0, 1):
+            for c in (0, 1):
+                cfg = ib.NTTConfig(batch_size=batch, coset_gen=g["coset_arb"].reshape(-1) if c else None)
+                y = ib.ntt(field, x, 1 << logn, d, cfg)
+                key = f"l{logn}_b{batch}_d{d}_c{c}"
+                assert hashlib.sha256(np.ascontiguousarray(y, dtype=np.uint32).tobytes()).digest() == g["sha_" + key].tobytes(), key
+                if "out_" + key in g.files:
+                    assert np.array_equal(y, g["out_" + key]), key
+    ib.ntt_release_domain(field)

@@ -128,3 +128,60 @@ def test_errors(domains):
         ib.ntt(field, X[:24], 24, ib.NTTDir.kForward)  # not a power of two (cpu_ntt_main.h:38)
     with pytest.raises(ib.IcicleError):
         ib.ntt_init_domain(ib.Field.BN254_FQ, X[0])  # field without an NTT in the reference
+
+
+@pytest.mark.parametrize("field,name,dom_log", [(ib.Field.BABYBEAR, "babybear", 24), (ib.Field.KOALABEAR, "koalabear", 22)])
+def test_small_field_tile_pass(field, name, dom_log):
+    """The dedicated 4-byte-field pass (csrc/ntt31.cuh, natural order in/out, n >= 2^10) against (a) the oracle port on every
+    pass-count / stage-split shape (2^10 .. 2^19: 2 passes of 5..9 stages, 3 passes at 2^19), (b) the generic tile kernel
+    (B200_NTT31_OFF=1) bit for bit at 2^20 x 4, in place and out of place, (c) inverse(forward(x)) == x at the domain size."""
+    import os
+    import port
+    import torch
+    fp = utils.field_params(name)
+    p = fp["p"]
+    ib.ntt_release_domain(field)
+    ib.ntt_init_domain(field, utils.to_limbs([omega(name, dom_log)], 1)[0])
+    rng = random.Random(5)
+    g = 0x7654321 % p
+    for logn in (10, 11, 12, 13, 14, 15, 16, 17, 18, 19):
+        n = 1 << logn
+        batch = 3 if logn <= 12 else 1
+        x = np.array([rng.randrange(p) for _ in range(n * batch)], dtype=np.uint32).reshape(-1, 1)
+        w = omega(name, logn)
+        for inverse, coset in ((False, 1), (True, 1), (False, g), (True, g)):
+            if logn >= 17 and coset != 1 and inverse:
+                continue  # keep the CPU oracle time bounded
+            exp = []
+            for b in range(batch):
+                exp += port.ntt([int(v) for v in x[b * n:(b + 1) * n, 0]], w, p, inverse=inverse, coset=coset, field_name=name)
+            cfg = ib.NTTConfig(batch_size=batch, coset_gen=utils.to_limbs([coset], 1)[0] if coset != 1 else None)
+            got = ib.ntt(field, x, n, ib.NTTDir.kInverse if inverse else ib.NTTDir.kForward, cfg)
+            assert got.reshape(-1).tolist() == exp, (name, logn, inverse, coset)
+    # (b) new pass vs the generic tile kernel
+    logn, batch = 20, 4
+    n = 1 << logn
+    xd = torch.randint(0, p, (n * batch,), dtype=torch.int64, device="cuda").to(torch.int32).contiguous()
+    for d in (ib.NTTDir.kForward, ib.NTTDir.kInverse):
+        cfg = lambda: ib.NTTConfig(batch_size=batch, is_async=False, coset_gen=utils.to_limbs([g], 1)[0])
+        y_new = ib.device_empty(n * batch)
+        ib.ntt(field, xd, n, d, cfg(), y_new)
+        inplace = xd.clone()
+        ib.ntt(field, inplace, n, d, cfg(), inplace)
+        os.environ["B200_NTT31_OFF"] = "1"
+        try:
+            y_old = ib.device_empty(n * batch)
+            ib.ntt(field, xd, n, d, cfg(), y_old)
+        finally:
+            del os.environ["B200_NTT31_OFF"]
+        assert torch.equal(y_new.view(-1), y_old.view(-1))
+        assert torch.equal(inplace.view(torch.int32).view(-1), y_new.view(torch.int32).view(-1))
+    # (c) round trip at the full domain size
+    n = 1 << dom_log
+    xd = torch.randint(0, p, (n,), dtype=torch.int64, device="cuda").to(torch.int32).contiguous()
+    y = ib.device_empty(n)
+    ib.ntt(field, xd, n, ib.NTTDir.kForward, ib.NTTConfig(), y)
+    z = ib.device_empty(n)
+    ib.ntt(field, y, n, ib.NTTDir.kInverse, ib.NTTConfig(), z)
+    assert torch.equal(z.view(torch.int32).view(-1), xd.view(-1))
+    ib.ntt_release_domain(field)

@@ -145,3 +145,30 @@ def test_port_vs_golden_other_curves():
             assert port.ntt(x[:64], w, fp["p"], inverse=bool(d), field_name=field) == utils.from_limbs(g[f"ntt_d{d}_o0"].reshape(-1, L))
             gc = utils.from_limbs(g["coset_arb"].reshape(1, -1))[0]
             assert port.ntt(x[:64], w, fp["p"], inverse=bool(d), coset=gc, field_name=field) == utils.from_limbs(g[f"ntt_d{d}_coset_arb"].reshape(-1, L))
+
+
+@pytest.mark.parametrize("name", ["babybear", "koalabear"])
+def test_port_ntt_small_fields_vs_reference_golden(name):
+    """tests/golden/<field>_ntt_big.npz (tools/make_golden_smallfield.py, outputs of the unmodified reference CPU backend):
+    the C restatement must reproduce them bit for bit -- full outputs at 2^10 / 2^11, SHA-256 of the output bytes at 2^13."""
+    import hashlib
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}_ntt_big.npz"))
+    fp = utils.field_params(name)
+    p = fp["p"]
+    root = int(g["ntt_root"][0])
+    dom_log = int(g["dom_log"][0])
+    coset = int(g["coset_arb"][0])
+    for logn, batch in ((10, 1), (11, 3), (13, 2)):
+        n = 1 << logn
+        rs = np.random.RandomState(1000 + logn)
+        x = rs.randint(0, p, size=(batch << logn, 1), dtype=np.int64).astype(np.uint32)
+        w = pow(root, 1 << (dom_log - logn), p)
+        for d in (0, 1):
+            for c in (0, 1):
+                rows = [port.ntt([int(v) for v in x[b * n:(b + 1) * n, 0]], w, p, inverse=bool(d), coset=coset if c else 1, field_name=name)
+                        for b in range(batch)]
+                y = np.array([v for row in rows for v in row], dtype=np.uint32).reshape(-1, 1)
+                key = f"l{logn}_b{batch}_d{d}_c{c}"
+                assert hashlib.sha256(y.tobytes()).digest() == g["sha_" + key].tobytes(), key
+                if "out_" + key in g.files:
+                    assert np.array_equal(y, g["out_" + key]), key
