@@ -782,7 +782,7 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
   // 4-byte fields, natural order in and out: dedicated 32-column tile pass (ntt31.cuh), 5..9 stages per pass
   bool fast31 = false;
   if constexpr (F::N == 1) {
-    fast31 = (cfg->ext_ntt_algorithm != B200_NTT_ALG_RADIX2) && !cfg->columns_batch && scatter_out && !gather_in && n_log >= 10 &&
+    fast31 = (cfg->ext_ntt_algorithm != B200_NTT_ALG_RADIX2) && !cfg->columns_batch && !gather_in && n_log >= 10 &&
              !getenv("B200_NTT31_OFF");
     if (fast31) {
       max_s = 9;
@@ -880,7 +880,9 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
     } else {
       dstp = work;
     }
-    if (use_tiles) {
+    if (fast31) {
+      if ((err = launch_ntt31<F>(src, dstp, p, r, s))) return err;
+    } else if (use_tiles) {
       if ((err = launch_tile_pass<F>(src, dstp, p, r, s))) return err;
     } else if ((err = launch_pass_r<F>(r, src, dstp, p, s))) {
       return err;

@@ -15,7 +15,8 @@
 //     the last round, by power iteration per lane (one table look-up per lane and pass);
 //   * the pass writes in the autosort layout of ntt.cu (digit written in natural frequency order just above the digits
 //     transformed so far), choosing lane = frequency for the first pass and lane = column afterwards so that stores are
-//     128-byte runs too.  Natural-order input and output (kNN), any batch, coset and inverse scaling folded in.
+//     128-byte runs too.  Natural-order input (kNN; k_ntt31) or the in-place schedule with bit-reversed output (kNR / kNM;
+//     k_ntt31_inplace, natural rows + DIF rounds), any batch, coset and inverse scaling folded in.
 // Reference semantics: icicle/backend/cpu/include/ntt_cpu.h:69-232 (see ntt.cu header); results are canonical field
 // elements, hence bit-identical to the reference whatever the schedule.
 #pragma once
@@ -24,7 +25,8 @@
 constexpr int NTT31_THREADS = 256;
 constexpr int NTT31_ROWPAD = 33;
 
-template <class F, int Q>
+// FIRST: the round starts at stage 0 (a == 0, blow == 0), where the twiddles with jj == 0 are all 1: 7 of its 12 products vanish.
+template <class F, int Q, bool FIRST>
 __device__ __forceinline__ void ntt31_dit_group(F (&e)[8], uint32_t a, uint32_t blow, const uint32_t* __restrict__ twsm, uint32_t S)
 {
   // Q decimation-in-time stages t = a .. a+Q-1 on the 2^Q rows base + (j << a); blow = base mod 2^a.
@@ -34,12 +36,13 @@ __device__ __forceinline__ void ntt31_dit_group(F (&e)[8], uint32_t a, uint32_t 
     const uint32_t t = a + i;
 #pragma unroll
     for (int jj = 0; jj < (1 << i); jj++) {
+      const bool trivial = FIRST && jj == 0;
       F w;
-      w.v[0] = twsm[(blow + ((uint32_t)jj << a)) << (S - 1 - t)];
+      if (!trivial) w.v[0] = twsm[(blow + ((uint32_t)jj << a)) << (S - 1 - t)];
 #pragma unroll
       for (int up = 0; up < (1 << (Q - 1 - i)); up++) {
         const int j0 = (up << (i + 1)) | jj, j1 = j0 | (1 << i);
-        const F u = e[j0], v = e[j1] * w;
+        const F u = e[j0], v = trivial ? e[j1] : e[j1] * w;
         e[j0] = u + v;
         e[j1] = u - v;
       }
@@ -59,8 +62,78 @@ __device__ __forceinline__ F ntt31_pow(F b, uint32_t ex)
   return r;
 }
 
+// Q decimation-in-frequency stages t = a+Q-1 .. a on the rows base + (j << a) (in-place schedule: natural rows in, the
+// frequency k ends up at row rev_S(k), which is where that schedule wants it).  LASTR: the round ends at stage 0 (a == 0), where
+// the twiddles with jj == 0 are 1.
+template <class F, int Q, bool LASTR>
+__device__ __forceinline__ void ntt31_dif_group(F (&e)[8], uint32_t a, uint32_t blow, const uint32_t* __restrict__ twsm, uint32_t S)
+{
+#pragma unroll
+  for (int i = Q - 1; i >= 0; i--) {
+    const uint32_t t = a + i;
+#pragma unroll
+    for (int jj = 0; jj < (1 << i); jj++) {
+      const bool trivial = LASTR && jj == 0;
+      F w;
+      if (!trivial) w.v[0] = twsm[(blow + ((uint32_t)jj << a)) << (S - 1 - t)];
+#pragma unroll
+      for (int up = 0; up < (1 << (Q - 1 - i)); up++) {
+        const int j0 = (up << (i + 1)) | jj, j1 = j0 | (1 << i);
+        const F u = e[j0], v = e[j1];
+        e[j0] = u + v;
+        e[j1] = trivial ? (u - v) : (u - v) * w;
+      }
+    }
+  }
+}
+
+// DIF round over the whole tile.  LASTR (a == 0): rows r = (b << Q) + j hold frequency k = (rev_Q(j) << (S-Q)) | rev_(S-Q)(b);
+// the inter-pass factor g1^k = T_b' * G^rev_Q(j) with b' = rev(b), G = g1^(2^(S-Q)); warps walk b' so that T advances by g1^8.
+template <class F, int Q, bool LASTR>
+__device__ __forceinline__ void ntt31_dif_round(uint32_t* __restrict__ tile, const uint32_t* __restrict__ twsm, uint32_t S, uint32_t a, uint32_t lane,
+                                                uint32_t warp, bool interpass, F g1)
+{
+  constexpr int NW = NTT31_THREADS / 32;
+  const uint32_t ngroups = 1u << (S - Q);
+  F G = F::one(), T = F::one(), g8 = F::one();
+  if (LASTR && interpass) {
+    G = g1;
+    for (uint32_t i = 0; i < S - Q; i++) G = G * G;
+    T = ntt31_pow(g1, warp);
+    g8 = ntt31_pow(g1, NW);
+  }
+  for (uint32_t gi = warp; gi < ngroups; gi += NW) {
+    const uint32_t g = LASTR ? (__brev(gi) >> (32 - (S - Q))) : gi; // LASTR: gi is b' = rev(b)
+    const uint32_t blow = g & ((1u << a) - 1);
+    const uint32_t base = ((g >> a) << (a + Q)) | blow;
+    F e[8];
+#pragma unroll
+    for (int j = 0; j < (1 << Q); j++) e[j].v[0] = tile[(base + ((uint32_t)j << a)) * NTT31_ROWPAD + lane];
+    ntt31_dif_group<F, Q, LASTR>(e, a, blow, twsm, S);
+    if (LASTR && interpass) {
+      F pw[1 << Q];
+      F t = T;
+#pragma unroll
+      for (int j = 0; j < (1 << Q); j++) {
+        pw[j] = t;
+        if (j + 1 < (1 << Q)) t = t * G;
+      }
+#pragma unroll
+      for (int j = 0; j < (1 << Q); j++) {
+        int rj = 0;
+#pragma unroll
+        for (int b = 0; b < Q; b++) rj |= ((j >> b) & 1) << (Q - 1 - b);
+        e[j] = e[j] * pw[rj];
+      }
+      T = T * g8;
+    }
+#pragma unroll
+    for (int j = 0; j < (1 << Q); j++) tile[(base + ((uint32_t)j << a)) * NTT31_ROWPAD + lane] = e[j].v[0];
+  }
+}
+
 // One round of Q stages over the whole tile.  LAST: apply the inter-pass twiddle (per lane l, per row k) before storing.
-template <class F, int Q, bool LAST>
+template <class F, int Q, bool LAST, bool FIRST>
 __device__ __forceinline__ void ntt31_round(uint32_t* __restrict__ tile, const uint32_t* __restrict__ twsm, uint32_t S, uint32_t a, uint32_t lane,
                                             uint32_t warp, bool interpass, F g1)
 {
@@ -80,7 +153,7 @@ __device__ __forceinline__ void ntt31_round(uint32_t* __restrict__ tile, const u
     F e[8];
 #pragma unroll
     for (int j = 0; j < (1 << Q); j++) e[j].v[0] = tile[(base + ((uint32_t)j << a)) * NTT31_ROWPAD + lane];
-    ntt31_dit_group<F, Q>(e, a, blow, twsm, S);
+    ntt31_dit_group<F, Q, FIRST>(e, a, blow, twsm, S);
     if (LAST && interpass) {
       F t = T;
 #pragma unroll
@@ -168,12 +241,14 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31(const uint32_t* __re
   while (a < S) {
     const uint32_t q = (S - a >= 3) ? 3 : (S - a);
     const bool last = (a + q == S);
-    if (last) {
-      if (q == 3) ntt31_round<F, 3, true>(tile, twsm, S, a, lane, warp, interpass, g1);
-      else if (q == 2) ntt31_round<F, 2, true>(tile, twsm, S, a, lane, warp, interpass, g1);
-      else ntt31_round<F, 1, true>(tile, twsm, S, a, lane, warp, interpass, g1);
+    if (last) { // S >= 5: the last round is never the first
+      if (q == 3) ntt31_round<F, 3, true, false>(tile, twsm, S, a, lane, warp, interpass, g1);
+      else if (q == 2) ntt31_round<F, 2, true, false>(tile, twsm, S, a, lane, warp, interpass, g1);
+      else ntt31_round<F, 1, true, false>(tile, twsm, S, a, lane, warp, interpass, g1);
+    } else if (a == 0) {
+      ntt31_round<F, 3, false, true>(tile, twsm, S, a, lane, warp, false, g1);
     } else {
-      ntt31_round<F, 3, false>(tile, twsm, S, a, lane, warp, false, g1);
+      ntt31_round<F, 3, false, false>(tile, twsm, S, a, lane, warp, false, g1);
     }
     a += q;
     __syncthreads();
@@ -220,6 +295,144 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31(const uint32_t* __re
   }
 }
 
+// In-place schedule (output bit-reversed: kNR / kNM, ntt.cu): the pass transforms the digit at bits [lo, lo+S) where it
+// lies.  lo >= 5: the 32 tile columns are the 32 lowest position bits (lane = column).  lo == 0 (the last pass): the tile is one
+// contiguous run of 32 * 2^S elements (lane = row).  Natural rows + DIF rounds leave frequency k at row rev_S(k), as the schedule wants.
+template <class F>
+__global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31_inplace(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassParams p, uint32_t S)
+{
+  static_assert(F::N == 1, "k_ntt31_inplace is the 4-byte-field pass");
+  extern __shared__ uint32_t sm[];
+  uint32_t* tile = sm;
+  uint32_t* twsm = sm + ((size_t)NTT31_ROWPAD << S);
+  constexpr int NW = NTT31_THREADS / 32;
+  const uint32_t T = threadIdx.x, lane = T & 31, warp = T >> 5;
+  const uint32_t n_log = p.n_log, lo = p.lo;
+  const uint64_t ntt_mask = (1ull << n_log) - 1;
+  const uint64_t dom_mask = (1ull << p.dom_log) - 1;
+  const uint32_t rev_shift = 64 - n_log;
+  const uint64_t col0 = (uint64_t)blockIdx.x * 32;
+  const uint32_t nrows = 1u << S;
+  const bool by_col = (lo != 0);
+  const uint64_t colg = col0 + lane;
+  const uint64_t lomask = (1ull << lo) - 1;
+  const uint64_t col_base = by_col ? (((colg >> lo) << (lo + S)) | (colg & lomask)) : 0; // position of (row 0, this lane's column)
+
+  for (uint32_t j = T; j < (1u << (S - 1)); j += NTT31_THREADS) {
+    uint64_t ex = (uint64_t)j << (p.dom_log - S);
+    if (p.inverse) ex = (0 - ex) & dom_mask;
+    twsm[j] = load_twiddle<F>(p.tw, ex).v[0];
+  }
+  constexpr int LD = 8;
+  if (by_col) {
+    for (uint32_t m0 = warp; m0 < nrows; m0 += NW * LD) {
+      uint32_t v[LD];
+#pragma unroll
+      for (int u = 0; u < LD; u++) {
+        const uint32_t m = m0 + u * NW;
+        v[u] = (m < nrows) ? src[col_base | ((uint64_t)m << lo)] : 0u;
+      }
+      if (p.in_mul) {
+#pragma unroll
+        for (int u = 0; u < LD; u++) {
+          const uint32_t m = m0 + u * NW;
+          if (m < nrows) {
+            F x, c;
+            x.v[0] = v[u];
+            c.v[0] = p.in_mul[(col_base | ((uint64_t)m << lo)) & ntt_mask];
+            v[u] = (x * c).v[0];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < LD; u++) {
+        const uint32_t m = m0 + u * NW;
+        if (m < nrows) tile[m * NTT31_ROWPAD + lane] = v[u];
+      }
+    }
+  } else {
+    const uint32_t ntask = 32u * (nrows >> 5); // (column, 32-row block)
+    for (uint32_t t0 = warp; t0 < ntask; t0 += NW * LD) {
+      uint32_t v[LD];
+#pragma unroll
+      for (int u = 0; u < LD; u++) {
+        const uint32_t task = t0 + u * NW;
+        const uint32_t c = task & 31, m = ((task >> 5) << 5) | lane;
+        const uint64_t pos = ((col0 + c) << S) | m;
+        v[u] = (task < ntask) ? src[pos] : 0u;
+        if (task < ntask && p.in_mul) {
+          F x, cc;
+          x.v[0] = v[u];
+          cc.v[0] = p.in_mul[pos & ntt_mask];
+          v[u] = (x * cc).v[0];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < LD; u++) {
+        const uint32_t task = t0 + u * NW;
+        const uint32_t c = task & 31, m = ((task >> 5) << 5) | lane;
+        if (task < ntask) tile[m * NTT31_ROWPAD + c] = v[u];
+      }
+    }
+  }
+  const bool interpass = (lo > 0);
+  F g1 = F::one();
+  if (interpass) {
+    const uint64_t l = colg & lomask;
+    uint64_t ex = (l << (p.dom_log - (lo + S))) & dom_mask;
+    if (p.inverse) ex = (0 - ex) & dom_mask;
+    g1 = load_twiddle<F>(p.tw, ex);
+  }
+  __syncthreads();
+
+  // ---- DIF rounds, top stages first; the last round covers stages [0, q0) with q0 = S mod 3 (or 3) ----
+  {
+    const uint32_t q0 = (S % 3 == 0) ? 3 : (S % 3);
+    uint32_t a = S;
+    while (a > q0) {
+      a -= 3;
+      ntt31_dif_round<F, 3, false>(tile, twsm, S, a, lane, warp, false, g1);
+      __syncthreads();
+    }
+    if (q0 == 3) ntt31_dif_round<F, 3, true>(tile, twsm, S, 0, lane, warp, interpass, g1);
+    else if (q0 == 2) ntt31_dif_round<F, 2, true>(tile, twsm, S, 0, lane, warp, interpass, g1);
+    else ntt31_dif_round<F, 1, true>(tile, twsm, S, 0, lane, warp, interpass, g1);
+    __syncthreads();
+  }
+
+  // ---- store in place; the last pass applies N^-1 / the inverse-coset table (indexed by the logical output index) ----
+  F scale = F::one();
+  const bool has_scale = p.last && !p.out_mul && p.out_scale;
+  if (has_scale) scale.v[0] = p.out_scale[0];
+  if (by_col) {
+    for (uint32_t m = warp; m < nrows; m += NW) {
+      const uint64_t pos = col_base | ((uint64_t)m << lo);
+      uint32_t v = tile[m * NTT31_ROWPAD + lane];
+      if (p.last) {
+        F x, mm;
+        x.v[0] = v;
+        if (p.out_mul) { mm.v[0] = p.out_mul[__brevll(pos & ntt_mask) >> rev_shift]; v = (x * mm).v[0]; }
+        else if (has_scale) v = (x * scale).v[0];
+      }
+      dst[pos] = v;
+    }
+  } else {
+    const uint32_t ntask = 32u * (nrows >> 5);
+    for (uint32_t task = warp; task < ntask; task += NW) {
+      const uint32_t c = task & 31, m = ((task >> 5) << 5) | lane;
+      const uint64_t pos = ((col0 + c) << S) | m;
+      uint32_t v = tile[m * NTT31_ROWPAD + c];
+      if (p.last) {
+        F x, mm;
+        x.v[0] = v;
+        if (p.out_mul) { mm.v[0] = p.out_mul[__brevll(pos & ntt_mask) >> rev_shift]; v = (x * mm).v[0]; }
+        else if (has_scale) v = (x * scale).v[0];
+      }
+      dst[pos] = v;
+    }
+  }
+}
+
 template <class F>
 int launch_ntt31(const uint32_t* src, uint32_t* dst, const PassParams& p, int S, cudaStream_t s)
 {
@@ -228,8 +441,13 @@ int launch_ntt31(const uint32_t* src, uint32_t* dst, const PassParams& p, int S,
     const uint64_t total_cols = total >> S;
     const uint64_t blocks = total_cols / 32; // n_log - S >= 5: always a whole number of 32-column tiles
     const size_t smem = (((size_t)NTT31_ROWPAD << S) + ((size_t)1 << (S - 1))) * 4;
-    B200_CUDA_TRY(cudaFuncSetAttribute(k_ntt31<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), B200_UNKNOWN_ERROR);
-    k_ntt31<F><<<(unsigned)blocks, NTT31_THREADS, smem, s>>>(src, dst, p, (uint32_t)S); B200_LAUNCHED(1);
+    if (p.rot) {
+      B200_CUDA_TRY(cudaFuncSetAttribute(k_ntt31<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), B200_UNKNOWN_ERROR);
+      k_ntt31<F><<<(unsigned)blocks, NTT31_THREADS, smem, s>>>(src, dst, p, (uint32_t)S); B200_LAUNCHED(1);
+    } else {
+      B200_CUDA_TRY(cudaFuncSetAttribute(k_ntt31_inplace<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), B200_UNKNOWN_ERROR);
+      k_ntt31_inplace<F><<<(unsigned)blocks, NTT31_THREADS, smem, s>>>(src, dst, p, (uint32_t)S); B200_LAUNCHED(1);
+    }
     B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     return B200_SUCCESS;
   } else {

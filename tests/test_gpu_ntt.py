@@ -158,6 +158,17 @@ def test_small_field_tile_pass(field, name, dom_log):
             cfg = ib.NTTConfig(batch_size=batch, coset_gen=utils.to_limbs([coset], 1)[0] if coset != 1 else None)
             got = ib.ntt(field, x, n, ib.NTTDir.kInverse if inverse else ib.NTTDir.kForward, cfg)
             assert got.reshape(-1).tolist() == exp, (name, logn, inverse, coset)
+    # bit-reversed output (kNR: the in-place schedule, k_ntt31_inplace) is the same data permuted; inverse + coset too
+    for logn, batch in ((10, 2), (13, 1), (14, 3), (16, 1), (19, 1)):
+        n = 1 << logn
+        x = np.array([rng.randrange(p) for _ in range(n * batch)], dtype=np.uint32).reshape(-1, 1)
+        perm = np.array([common.bitrev(i, logn) for i in range(n)])
+        perm_b = np.concatenate([perm + b * n for b in range(batch)])
+        for d, coset in ((ib.NTTDir.kForward, 1), (ib.NTTDir.kInverse, g), (ib.NTTDir.kForward, g)):
+            cg = utils.to_limbs([coset], 1)[0] if coset != 1 else None
+            nn = ib.ntt(field, x, n, d, ib.NTTConfig(batch_size=batch, coset_gen=cg, ordering=ib.Ordering.kNN))
+            nr = ib.ntt(field, x, n, d, ib.NTTConfig(batch_size=batch, coset_gen=cg, ordering=ib.Ordering.kNR))
+            assert np.array_equal(nr, nn[perm_b]), (name, logn, d, coset)
     # (b) new pass vs the generic tile kernel
     logn, batch = 20, 4
     n = 1 << logn
