@@ -25,6 +25,25 @@
 constexpr int NTT31_THREADS = 256;
 constexpr int NTT31_ROWPAD = 33;
 
+// Branch-free arithmetic for p < 2^31 on canonical values in [0, p): a conditional +-p is the unsigned minimum of the two
+// candidates (the wrong one wraps past 2^32 - p > p), so an add or sub is 3 ALU instructions and the Montgomery product is
+// 2 IMAD.WIDE + 1 IMAD + 2 ALU.  Same values as Fp<P>::operator+,-,* (ff.cuh); only the instruction selection differs.
+template <class F>
+struct A31 {
+  static constexpr uint32_t P = F::P::p(0);
+  static constexpr uint32_t NP0 = F::P::NP0;
+  static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { const uint32_t s = a + b; return min(s, s - P); }
+  static __device__ __forceinline__ uint32_t sub(uint32_t a, uint32_t b) { const uint32_t d = a - b; return min(d, d + P); }
+  static __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) // a * b * 2^-32 mod p (b usually a Montgomery-form twiddle)
+  {
+    uint64_t t = (uint64_t)a * b;
+    const uint32_t m = (uint32_t)t * NP0;
+    t += (uint64_t)m * P; // low word becomes 0; < 2^62 + 2^63, no overflow
+    const uint32_t r = (uint32_t)(t >> 32);
+    return min(r, r - P);
+  }
+};
+
 // FIRST: the round starts at stage 0 (a == 0, blow == 0), where the twiddles with jj == 0 are all 1: 7 of its 12 products vanish.
 template <class F, int Q, bool FIRST>
 __device__ __forceinline__ void ntt31_dit_group(F (&e)[8], uint32_t a, uint32_t blow, const uint32_t* __restrict__ twsm, uint32_t S)
@@ -42,9 +61,9 @@ __device__ __forceinline__ void ntt31_dit_group(F (&e)[8], uint32_t a, uint32_t 
 #pragma unroll
       for (int up = 0; up < (1 << (Q - 1 - i)); up++) {
         const int j0 = (up << (i + 1)) | jj, j1 = j0 | (1 << i);
-        const F u = e[j0], v = trivial ? e[j1] : e[j1] * w;
-        e[j0] = u + v;
-        e[j1] = u - v;
+        const uint32_t u = e[j0].v[0], v = trivial ? e[j1].v[0] : A31<F>::mul(e[j1].v[0], w.v[0]);
+        e[j0].v[0] = A31<F>::add(u, v);
+        e[j1].v[0] = A31<F>::sub(u, v);
       }
     }
   }
@@ -79,9 +98,10 @@ __device__ __forceinline__ void ntt31_dif_group(F (&e)[8], uint32_t a, uint32_t 
 #pragma unroll
       for (int up = 0; up < (1 << (Q - 1 - i)); up++) {
         const int j0 = (up << (i + 1)) | jj, j1 = j0 | (1 << i);
-        const F u = e[j0], v = e[j1];
-        e[j0] = u + v;
-        e[j1] = trivial ? (u - v) : (u - v) * w;
+        const uint32_t u = e[j0].v[0], v = e[j1].v[0];
+        e[j0].v[0] = A31<F>::add(u, v);
+        const uint32_t d = A31<F>::sub(u, v);
+        e[j1].v[0] = trivial ? d : A31<F>::mul(d, w.v[0]);
       }
     }
   }
@@ -116,16 +136,16 @@ __device__ __forceinline__ void ntt31_dif_round(uint32_t* __restrict__ tile, con
 #pragma unroll
       for (int j = 0; j < (1 << Q); j++) {
         pw[j] = t;
-        if (j + 1 < (1 << Q)) t = t * G;
+        if (j + 1 < (1 << Q)) t.v[0] = A31<F>::mul(t.v[0], G.v[0]);
       }
 #pragma unroll
       for (int j = 0; j < (1 << Q); j++) {
         int rj = 0;
 #pragma unroll
         for (int b = 0; b < Q; b++) rj |= ((j >> b) & 1) << (Q - 1 - b);
-        e[j] = e[j] * pw[rj];
+        e[j].v[0] = A31<F>::mul(e[j].v[0], pw[rj].v[0]);
       }
-      T = T * g8;
+      T.v[0] = A31<F>::mul(T.v[0], g8.v[0]);
     }
 #pragma unroll
     for (int j = 0; j < (1 << Q); j++) tile[(base + ((uint32_t)j << a)) * NTT31_ROWPAD + lane] = e[j].v[0];
@@ -158,10 +178,10 @@ __device__ __forceinline__ void ntt31_round(uint32_t* __restrict__ tile, const u
       F t = T;
 #pragma unroll
       for (int j = 0; j < (1 << Q); j++) {
-        e[j] = e[j] * t;
-        if (j + 1 < (1 << Q)) t = t * G;
+        e[j].v[0] = A31<F>::mul(e[j].v[0], t.v[0]);
+        if (j + 1 < (1 << Q)) t.v[0] = A31<F>::mul(t.v[0], G.v[0]);
       }
-      T = T * g8;
+      T.v[0] = A31<F>::mul(T.v[0], g8.v[0]);
     }
 #pragma unroll
     for (int j = 0; j < (1 << Q); j++) tile[(base + ((uint32_t)j << a)) * NTT31_ROWPAD + lane] = e[j].v[0];
@@ -197,25 +217,19 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31(const uint32_t* __re
   {
     const uint32_t nrows = 1u << S;
     constexpr int LD = 8; // independent 128-byte row loads in flight per warp
+    const uint32_t* __restrict__ srow = src + (hi_part | lowfull);
     for (uint32_t m0 = warp; m0 < nrows; m0 += NW * LD) {
       uint32_t v[LD];
 #pragma unroll
       for (int u = 0; u < LD; u++) {
         const uint32_t m = m0 + u * NW;
-        const uint64_t pos = hi_part | ((uint64_t)m << rsh) | lowfull;
-        v[u] = (m < nrows) ? src[pos] : 0u;
+        v[u] = (m < nrows) ? srow[m << rsh] : 0u; // (m << rsh) < 2^n_log: a 32-bit offset from this lane's row-0 element
       }
       if (p.in_mul) {
 #pragma unroll
         for (int u = 0; u < LD; u++) {
           const uint32_t m = m0 + u * NW;
-          if (m < nrows) {
-            const uint64_t pin = (((uint64_t)m << rsh) | lowfull) & ntt_mask;
-            F x, c;
-            x.v[0] = v[u];
-            c.v[0] = p.in_mul[pin];
-            v[u] = (x * c).v[0];
-          }
+          if (m < nrows) v[u] = A31<F>::mul(v[u], p.in_mul[(m << rsh) | (uint32_t)lowfull]);
         }
       }
 #pragma unroll
@@ -257,40 +271,35 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31(const uint32_t* __re
   // ---- store in the autosort layout: idx = batch | (untransformed << (S+done)) | (k << done) | (transformed so far) ----
   const uint32_t done = p.done;
   const uint32_t nrows = 1u << S;
+  F scale = F::one();
+  const bool has_scale = p.last && !p.out_mul && p.out_scale;
+  if (has_scale) scale.v[0] = p.out_scale[0];
   if (done == 0) {
-    // first pass: each column is a contiguous run of 2^S frequencies -> lane = frequency
-    for (uint32_t task = warp; task < 32u * (nrows >> 5); task += NW) {
+    // first pass: column c of the tile is the contiguous run [(lowfull0 + c) << S, +2^S) -> lane = frequency
+    const uint64_t base0 = ((col0 >> rsh) << n_log) | ((col0 & rmask) << S);
+    uint32_t* __restrict__ drow = dst + base0 + lane;
+    const uint32_t ntask = 32u * (nrows >> 5);
+    for (uint32_t task = warp; task < ntask; task += NW) {
       const uint32_t c = task & 31, k = ((task >> 5) << 5) | lane;
-      const uint64_t colc = col0 + c;
-      const uint64_t lf = colc & rmask;
-      const uint64_t idx = ((colc >> rsh) << n_log) | (lf << S) | k;
+      const uint32_t off = (c << S) + ((task >> 5) << 5);
       uint32_t v = tile[k * NTT31_ROWPAD + c];
       if (p.last) {
-        const uint64_t kidx = idx & ntt_mask;
-        F x, m;
-        x.v[0] = v;
-        if (p.out_mul) { m.v[0] = p.out_mul[kidx]; v = (x * m).v[0]; }
-        else if (p.out_scale) { m.v[0] = p.out_scale[0]; v = (x * m).v[0]; }
+        if (p.out_mul) v = A31<F>::mul(v, p.out_mul[(base0 + off + lane) & ntt_mask]);
+        else if (has_scale) v = A31<F>::mul(v, scale.v[0]);
       }
-      dst[idx] = v;
+      drow[off] = v;
     }
   } else {
     // later passes (done >= 5): the 32 columns of a row stay adjacent -> lane = column
-    const uint64_t lo_done = lowfull & ((1ull << done) - 1);
-    const uint64_t up = (lowfull >> done) << (S + done);
-    F scale = F::one();
-    const bool has_scale = p.last && !p.out_mul && p.out_scale;
-    if (has_scale) scale.v[0] = p.out_scale[0];
+    const uint64_t base1 = hi_part | ((lowfull >> done) << (S + done)) | (lowfull & ((1ull << done) - 1));
+    uint32_t* __restrict__ drow = dst + base1;
     for (uint32_t k = warp; k < nrows; k += NW) {
-      const uint64_t idx = hi_part | up | ((uint64_t)k << done) | lo_done;
       uint32_t v = tile[k * NTT31_ROWPAD + lane];
       if (p.last) {
-        F x, m;
-        x.v[0] = v;
-        if (p.out_mul) { m.v[0] = p.out_mul[idx & ntt_mask]; v = (x * m).v[0]; }
-        else if (has_scale) v = (x * scale).v[0];
+        if (p.out_mul) v = A31<F>::mul(v, p.out_mul[(base1 | ((uint64_t)k << done)) & ntt_mask]);
+        else if (has_scale) v = A31<F>::mul(v, scale.v[0]);
       }
-      dst[idx] = v;
+      drow[k << done] = v;
     }
   }
 }
@@ -330,18 +339,13 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31_inplace(const uint32
 #pragma unroll
       for (int u = 0; u < LD; u++) {
         const uint32_t m = m0 + u * NW;
-        v[u] = (m < nrows) ? src[col_base | ((uint64_t)m << lo)] : 0u;
+        v[u] = (m < nrows) ? src[col_base + (m << lo)] : 0u;
       }
       if (p.in_mul) {
 #pragma unroll
         for (int u = 0; u < LD; u++) {
           const uint32_t m = m0 + u * NW;
-          if (m < nrows) {
-            F x, c;
-            x.v[0] = v[u];
-            c.v[0] = p.in_mul[(col_base | ((uint64_t)m << lo)) & ntt_mask];
-            v[u] = (x * c).v[0];
-          }
+          if (m < nrows) v[u] = A31<F>::mul(v[u], p.in_mul[(col_base + (m << lo)) & ntt_mask]);
         }
       }
 #pragma unroll
@@ -360,12 +364,7 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31_inplace(const uint32
         const uint32_t c = task & 31, m = ((task >> 5) << 5) | lane;
         const uint64_t pos = ((col0 + c) << S) | m;
         v[u] = (task < ntask) ? src[pos] : 0u;
-        if (task < ntask && p.in_mul) {
-          F x, cc;
-          x.v[0] = v[u];
-          cc.v[0] = p.in_mul[pos & ntt_mask];
-          v[u] = (x * cc).v[0];
-        }
+        if (task < ntask && p.in_mul) v[u] = A31<F>::mul(v[u], p.in_mul[pos & ntt_mask]);
       }
 #pragma unroll
       for (int u = 0; u < LD; u++) {
@@ -406,13 +405,11 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31_inplace(const uint32
   if (has_scale) scale.v[0] = p.out_scale[0];
   if (by_col) {
     for (uint32_t m = warp; m < nrows; m += NW) {
-      const uint64_t pos = col_base | ((uint64_t)m << lo);
+      const uint64_t pos = col_base + (m << lo);
       uint32_t v = tile[m * NTT31_ROWPAD + lane];
       if (p.last) {
-        F x, mm;
-        x.v[0] = v;
-        if (p.out_mul) { mm.v[0] = p.out_mul[__brevll(pos & ntt_mask) >> rev_shift]; v = (x * mm).v[0]; }
-        else if (has_scale) v = (x * scale).v[0];
+        if (p.out_mul) v = A31<F>::mul(v, p.out_mul[__brevll(pos & ntt_mask) >> rev_shift]);
+        else if (has_scale) v = A31<F>::mul(v, scale.v[0]);
       }
       dst[pos] = v;
     }
@@ -423,10 +420,8 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31_inplace(const uint32
       const uint64_t pos = ((col0 + c) << S) | m;
       uint32_t v = tile[m * NTT31_ROWPAD + c];
       if (p.last) {
-        F x, mm;
-        x.v[0] = v;
-        if (p.out_mul) { mm.v[0] = p.out_mul[__brevll(pos & ntt_mask) >> rev_shift]; v = (x * mm).v[0]; }
-        else if (has_scale) v = (x * scale).v[0];
+        if (p.out_mul) v = A31<F>::mul(v, p.out_mul[__brevll(pos & ntt_mask) >> rev_shift]);
+        else if (has_scale) v = A31<F>::mul(v, scale.v[0]);
       }
       dst[pos] = v;
     }
