@@ -312,6 +312,45 @@ def ntt(field, input, size, direction, config=None, output=None):
     return output
 
 
+EXTENSION_DEGREE = 4  # quartic extension of BabyBear / KoalaBear (fields/stark_fields/babybear.h:88-93)
+
+
+def ntt_extension(field, input, size, direction, config=None, output=None):
+    """icicle::ntt over extension_t (icicle/include/icicle/ntt.h:108 -> src/ntt.cpp:90-103, `<field>_extension_ntt`): `size`
+    quartic extension elements per transform, each 4 base-field coefficients; twiddles, coset generator and domain are the
+    scalar field's."""
+    cfg = copy.copy(config) if config else NTTConfig()
+    ip, i_dev, _ki = _ptr(input)
+    cfg.are_inputs_on_device = i_dev
+    w = field_limbs(field) * EXTENSION_DEGREE
+    if output is None:
+        n = size * cfg.batch_size * w
+        output = device_empty(n) if cfg.are_outputs_on_device else np.zeros((size * cfg.batch_size, w), dtype=np.uint32)
+    op, o_dev, _ko = _ptr(output)
+    cfg.are_outputs_on_device = o_dev
+    c = cfg._c()
+    check(lib.b200_ntt_extension(int(field), ip, int(size), int(direction), C.byref(c), op), "ntt_extension")
+    return output
+
+
+def ecntt(curve, input, size, direction, config=None, output=None):
+    """icicle::ntt over projective_t (icicle/include/icicle/ntt.h:108 -> src/ecntt.cpp:8-18, `<curve>_ecntt`): NTT of `size` G1
+    points (homogeneous projective, standard form) with the scalar field's twiddles; the scalar field's domain must be
+    initialised (ntt_init_domain on the curve's scalar field)."""
+    cfg = copy.copy(config) if config else NTTConfig()
+    ip, i_dev, _ki = _ptr(input)
+    cfg.are_inputs_on_device = i_dev
+    w = projective_limbs(curve)
+    if output is None:
+        n = size * cfg.batch_size * w
+        output = device_empty(n) if cfg.are_outputs_on_device else np.zeros((size * cfg.batch_size, w), dtype=np.uint32)
+    op, o_dev, _ko = _ptr(output)
+    cfg.are_outputs_on_device = o_dev
+    c = cfg._c()
+    check(lib.b200_ecntt(int(curve), ip, int(size), int(direction), C.byref(c), op), "ecntt")
+    return output
+
+
 # ---- vec ops ----------------------------------------------------------------------------------------------------------
 class VecOpsConfig:
     """icicle::VecOpsConfig (icicle/include/icicle/vec_ops.h:19-44)."""
@@ -535,8 +574,8 @@ def set_profiling(on):
 
 def last_profile():
     """(what, [(stage, ms), ...]) of the last call made while profiling was on."""
-    names = C.create_string_buffer(512)
-    ms = (C.c_float * 16)()
-    k = lib.b200_get_last_profile(names, 512, ms, 16)
+    names = C.create_string_buffer(2048)
+    ms = (C.c_float * 64)()
+    k = lib.b200_get_last_profile(names, 2048, ms, 64)
     parts = names.value.decode().split(",")
     return parts[0], [(parts[1 + i], float(ms[i])) for i in range(k)]

@@ -84,6 +84,8 @@ SYMBOLS = {
     "b200_ntt_release_domain": (_i, [_i]),
     "b200_ntt_get_root_of_unity_from_domain": (_i, [_i, _u64, _vp]),
     "b200_ntt": (_i, [_i, _vp, _i, _i, C.POINTER(NttConfigC), _vp]),
+    "b200_ntt_extension": (_i, [_i, _vp, _i, _i, C.POINTER(NttConfigC), _vp]),
+    "b200_ecntt": (_i, [_i, _vp, _i, _i, C.POINTER(NttConfigC), _vp]),
     "b200_vec_ops_default_config": (None, [C.POINTER(VecOpsConfigC)]),
     "b200_vec_op": (_i, [_i, _i, _vp, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
     "b200_vector_inv": (_i, [_i, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),

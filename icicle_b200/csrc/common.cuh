@@ -123,7 +123,7 @@ extern "C" B200_API void b200_count_launch(int n);
 struct StageTimer {
   // Records an event per stage boundary on the launching stream when profiling is on (b200_set_profiling);
   // b200_get_last_profile() reports the elapsed times of the last completed call.
-  static constexpr int MAX_STAGES = 12;
+  static constexpr int MAX_STAGES = 64;
   cudaEvent_t ev[MAX_STAGES + 1];
   const char* names[MAX_STAGES];
   int n = 0;

@@ -459,9 +459,13 @@ inline int choose_pair_levels(uint64_t max_ent, uint64_t max_buckets)
 
 // Device-resident core: scalars (standard or Montgomery form), points already in Montgomery form, results written to d_res
 // (device).  Everything is enqueued on `s`; nothing here synchronises.
+// `phases`: MSM_ACC = digits .. stitched bucket sums, MSM_RED = bucket reduction + final; the host-pointer pipeline
+// (msm_pipelined) runs MSM_ACC once per point-range chunk into `ext_bkt` (batch == 1) and MSM_RED once at the end.
+enum : int { MSM_ACC = 1, MSM_RED = 2, MSM_ALL = 3 };
+
 template <class C>
 int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPlan& pl, int batch, bool shared, const b200_msm_config* cfg,
-             void* d_res, cudaStream_t s, StageTimer& prof)
+             void* d_res, cudaStream_t s, StageTimer& prof, uint32_t* ext_bkt = nullptr, int phases = MSM_ALL)
 {
   typedef typename C::Scalar S;
   typedef typename C::Base F;
@@ -487,30 +491,37 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
   if (chunk_log > pl.c - 1) chunk_log = pl.c - 1;
   const uint64_t max_chunks = max_buckets >> chunk_log;
 
+  if (ext_bkt && (batch != 1 || chunk != 1)) return B200_INVALID_ARGUMENT;
+  const bool do_acc = (phases & MSM_ACC) != 0, do_red = (phases & MSM_RED) != 0;
   Scratch s_k0, s_k1, s_v0, s_v1, s_cub, s_bkt, s_pkey, s_pflag, s_ppt, s_pkey2, s_pflag2, s_ppt2, s_red0, s_red1;
-  if ((err = s_k0.alloc(max_ent * 4, s))) return err;
-  if ((err = s_k1.alloc(max_ent * 4, s))) return err;
-  if ((err = s_v0.alloc(max_ent * 4, s))) return err;
-  if ((err = s_v1.alloc(max_ent * 4, s))) return err;
   size_t cub_bytes = 0;
-  {
-    cub::DoubleBuffer<uint32_t> dk(s_k0.as<uint32_t>(), s_k1.as<uint32_t>()), dv(s_v0.as<uint32_t>(), s_v1.as<uint32_t>());
-    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, dk, dv, (int64_t)max_ent, 0, 32, s);
+  if (do_acc) {
+    if ((err = s_k0.alloc(max_ent * 4, s))) return err;
+    if ((err = s_k1.alloc(max_ent * 4, s))) return err;
+    if ((err = s_v0.alloc(max_ent * 4, s))) return err;
+    if ((err = s_v1.alloc(max_ent * 4, s))) return err;
+    {
+      cub::DoubleBuffer<uint32_t> dk(s_k0.as<uint32_t>(), s_k1.as<uint32_t>()), dv(s_v0.as<uint32_t>(), s_v1.as<uint32_t>());
+      cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, dk, dv, (int64_t)max_ent, 0, 32, s);
+    }
+    if ((err = s_cub.alloc(cub_bytes, s))) return err;
+    if ((err = s_pkey.alloc(max_slices * 2 * 4, s))) return err;
+    if ((err = s_pflag.alloc(max_slices * 2 * 4, s))) return err;
+    if ((err = s_ppt.alloc(max_slices * 2 * XW * 4, s))) return err;
+    const uint64_t max_slots2 = 2 * ((max_slices * 2 + 15) / 16) + 2;
+    if ((err = s_pkey2.alloc(max_slots2 * 4, s))) return err;
+    if ((err = s_pflag2.alloc(max_slots2 * 4, s))) return err;
+    if ((err = s_ppt2.alloc(max_slots2 * XW * 4, s))) return err;
   }
-  if ((err = s_cub.alloc(cub_bytes, s))) return err;
-  if ((err = s_bkt.alloc(max_buckets * XW * 4, s))) return err;
-  if ((err = s_pkey.alloc(max_slices * 2 * 4, s))) return err;
-  if ((err = s_pflag.alloc(max_slices * 2 * 4, s))) return err;
-  if ((err = s_ppt.alloc(max_slices * 2 * XW * 4, s))) return err;
-  const uint64_t max_slots2 = 2 * ((max_slices * 2 + 15) / 16) + 2;
-  if ((err = s_pkey2.alloc(max_slots2 * 4, s))) return err;
-  if ((err = s_pflag2.alloc(max_slots2 * 4, s))) return err;
-  if ((err = s_ppt2.alloc(max_slots2 * XW * 4, s))) return err;
-  if ((err = s_red0.alloc(std::max<uint64_t>(max_chunks, 1) * XW * 4, s))) return err;
-  if ((err = s_red1.alloc(std::max<uint64_t>(max_chunks / 2 + 1, 1) * XW * 4, s))) return err;
+  if (!ext_bkt && (err = s_bkt.alloc(max_buckets * XW * 4, s))) return err;
+  uint32_t* const bkt = ext_bkt ? ext_bkt : s_bkt.as<uint32_t>();
+  if (do_red) {
+    if ((err = s_red0.alloc(std::max<uint64_t>(max_chunks, 1) * XW * 4, s))) return err;
+    if ((err = s_red1.alloc(std::max<uint64_t>(max_chunks / 2 + 1, 1) * XW * 4, s))) return err;
+  }
 
   // ---- batched-affine pair levels (msm_pairs.cuh) ---------------------------------------------------------------------
-  int levels = choose_pair_levels(max_ent, max_buckets);
+  int levels = do_acc ? choose_pair_levels(max_ent, max_buckets) : 0;
   constexpr uint32_t PAIR_J = 32, INV_G = 64;
   const uint32_t nb_max = (uint32_t)max_buckets;
   uint64_t cap[10];
@@ -564,6 +575,7 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
     const uint32_t* sc = (const uint32_t*)d_scal + (uint64_t)b0 * n * S::N;
     const uint32_t* pts = pts_m + (shared ? 0 : (uint64_t)b0 * n * pl.pf * AW);
 
+    if (do_acc) {
     // K6
     {
       uint64_t th = (uint64_t)n * bl;
@@ -580,12 +592,12 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
     }
     prof.mark("sort");
     // K8
-    B200_CUDA_TRY(cudaMemsetAsync(s_bkt.p, 0, n_buckets * XW * 4, s), B200_UNKNOWN_ERROR);
+    B200_CUDA_TRY(cudaMemsetAsync(bkt, 0, n_buckets * XW * 4, s), B200_UNKNOWN_ERROR);
     uint64_t n_slices;
     if (levels == 0) {
       n_slices = (n_ent + slice - 1) / slice;
       k_accumulate<F, false><<<(unsigned)((n_slices + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
-        dk.Current(), dv.Current(), n_ent, nullptr, slice, sentinel, pts, s_bkt.as<uint32_t>(), s_pkey.as<uint32_t>(),
+        dk.Current(), dv.Current(), n_ent, nullptr, slice, sentinel, pts, bkt, s_pkey.as<uint32_t>(),
         s_pflag.as<uint32_t>(), s_ppt.as<uint32_t>(), n_slices); B200_LAUNCHED(1);
       B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     } else {
@@ -657,7 +669,7 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
       prof.mark("pair_levels");
       n_slices = (capl + slice - 1) / slice;
       k_accumulate<F, true><<<(unsigned)((n_slices + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
-        lk, nullptr, 0, s_off[levels & 1].as<uint32_t>() + nb, slice, 0xffffffffu, lp, s_bkt.as<uint32_t>(), s_pkey.as<uint32_t>(),
+        lk, nullptr, 0, s_off[levels & 1].as<uint32_t>() + nb, slice, 0xffffffffu, lp, bkt, s_pkey.as<uint32_t>(),
         s_pflag.as<uint32_t>(), s_ppt.as<uint32_t>(), n_slices); B200_LAUNCHED(1);
       B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     }
@@ -671,21 +683,23 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
       while (n_slots > 512) {
         const uint64_t nt = (n_slots + seg - 1) / seg;
         k_reduce_partials<F><<<(unsigned)((nt + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
-          ik, ifl, ipt, n_slots, seg, ok, ofl, opt, nt, s_bkt.as<uint32_t>()); B200_LAUNCHED(1);
+          ik, ifl, ipt, n_slots, seg, ok, ofl, opt, nt, bkt); B200_LAUNCHED(1);
         B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
         std::swap(ik, ok);
         std::swap(ifl, ofl);
         std::swap(ipt, opt);
         n_slots = 2 * nt;
       }
-      k_resolve<F><<<(unsigned)((n_slots + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(ik, ifl, ipt, n_slots, s_bkt.as<uint32_t>()); B200_LAUNCHED(1);
+      k_resolve<F><<<(unsigned)((n_slots + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(ik, ifl, ipt, n_slots, bkt); B200_LAUNCHED(1);
       B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     }
     prof.mark("resolve");
+    } // do_acc
+    if (!do_red) continue;
     // K9
     const uint64_t n_chunks = n_buckets >> chunk_log;
     k_bucket_chunks<F><<<(unsigned)((n_chunks + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
-      s_bkt.as<uint32_t>(), n_modules, (uint32_t)(pl.c - 1), (uint32_t)chunk_log, s_red0.as<uint32_t>()); B200_LAUNCHED(1);
+      bkt, n_modules, (uint32_t)(pl.c - 1), (uint32_t)chunk_log, s_red0.as<uint32_t>()); B200_LAUNCHED(1);
     B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     uint32_t* cur = s_red0.as<uint32_t>();
     uint32_t* other = s_red1.as<uint32_t>();
@@ -709,10 +723,27 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
 template <class F>
 __global__ void k_proj_sum(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out);
 
-// Host-pointer fast path (the reference-facing call with HOST scalars and points, i.e. what `e2e` measures): the MSM is cut into
-// point-range chunks; chunk i+1 is copied host->device on a private copy stream while chunk i runs on the caller's stream
-// (double-buffered staging, events in both directions), and the per-chunk partial results are summed by k_proj_sum.
-// PCIe (~55 GB/s) moves 96 B/point, so a 2^26 MSM is transfer-bound unless the copies hide behind the arithmetic.
+// dst[k] += src[k] over two XYZZ bucket arrays (host-pointer pipeline: per-chunk bucket sums into the running ones)
+template <class F>
+__global__ void __launch_bounds__(MSM_THREADS) k_bucket_merge(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t n)
+{
+  constexpr int XW = 4 * F::N;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  XYZZ<F> b = load_xyzz<F>(src + i * XW);
+  if (b.is_inf()) return;
+  XYZZ<F> a = load_xyzz<F>(dst + i * XW);
+  a.add(b);
+  store_xyzz<F>(dst + i * XW, a);
+}
+
+// Host-pointer fast path (the reference-facing call with HOST scalars and points, i.e. what `e2e` measures).  PCIe (~55 GB/s)
+// moves 96 B/point, so a 2^26 MSM is transfer-bound unless the copies hide behind the arithmetic.  The whole input gets a
+// device staging area (as the plain host path would allocate anyway); a private copy stream pushes it up chunk by chunk
+// without ever waiting for the compute stream, and the caller's stream runs digits -> sort -> bucket accumulation of chunk i
+// (MSM_ACC, window size chosen for the WHOLE msm) as soon as chunk i has landed.  Chunk 0 accumulates straight into the
+// running bucket array, later chunks into a second array that k_bucket_merge folds in; the bucket reduction + Horner
+// (MSM_RED) runs once at the end.  Exposed transfer time = the first chunk only.
 inline cudaStream_t copy_stream_for_current_device()
 {
   static thread_local cudaStream_t streams[64] = {};
@@ -723,64 +754,85 @@ inline cudaStream_t copy_stream_for_current_device()
   return streams[dev];
 }
 
+// B200_MSM_PIPELINE_MIN=<points> (tests): smallest host-pointer MSM that takes the pipeline, and the chunks may then be small
+inline uint32_t pipeline_min_points()
+{
+  if (const char* ev = getenv("B200_MSM_PIPELINE_MIN")) return (uint32_t)std::max(2, atoi(ev));
+  return 1u << 23;
+}
+
+inline uint32_t pipeline_chunks()
+{
+  uint32_t k = 8;
+  if (const char* ev = getenv("B200_MSM_PIPELINE_CHUNKS")) k = (uint32_t)std::max(1, std::min(32, atoi(ev)));
+  return k;
+}
+
 template <class C>
 int msm_pipelined(const void* scalars, const void* bases, uint32_t n, const b200_msm_config* cfg, void* results)
 {
   typedef typename C::Scalar S;
   typedef typename C::Base F;
   typedef typename base_fp<F>::type B;
-  constexpr int AW = 2 * F::N, PW = 3 * F::N;
+  constexpr int AW = 2 * F::N, XW = 4 * F::N, PW = 3 * F::N;
+  constexpr uint32_t MAX_CHUNKS = 32;
   cudaStream_t s = (cudaStream_t)cfg->stream;
   cudaStream_t cs = copy_stream_for_current_device();
   if (!cs) return B200_UNKNOWN_ERROR;
-  const uint32_t pf = cfg->precompute_factor > 0 ? cfg->precompute_factor : 1;
-  uint32_t chunk = 1u << 22;
-  while ((uint64_t)chunk * 4 < n) chunk <<= 1; // at most 4..8 chunks
+  b200_msm_config sub = *cfg;
+  sub.batch_size = 1;
+  const MsmPlan pl = make_plan<C>((int)n, &sub); // one window size for all chunks: they share the bucket array
+  const uint32_t pf = (uint32_t)pl.pf;
+  uint32_t chunk = (n + pipeline_chunks() - 1) / pipeline_chunks();
+  chunk = std::max<uint32_t>(chunk, getenv("B200_MSM_PIPELINE_MIN") ? 1u : (1u << 20));
   const uint32_t nchunks = (n + chunk - 1) / chunk;
+  if (nchunks > MAX_CHUNKS) return B200_INVALID_ARGUMENT;
+  const uint64_t n_buckets = (uint64_t)pl.nbm << (pl.c - 1);
   int err;
-  Scratch d_s[2], d_p[2], d_part, s_res;
-  for (int b = 0; b < 2; b++) {
-    if ((err = d_s[b].alloc((size_t)chunk * S::BYTES, s))) return err;
-    if ((err = d_p[b].alloc((size_t)chunk * pf * AW * 4, s))) return err;
-  }
-  if ((err = d_part.alloc((size_t)nchunks * PW * 4, s))) return err;
+  Scratch d_s, d_p, d_bkt, d_tmp, s_res;
+  if ((err = d_s.alloc((size_t)n * S::BYTES, s))) return err;
+  if ((err = d_p.alloc((size_t)n * pf * AW * 4, s))) return err;
+  if ((err = d_bkt.alloc((size_t)n_buckets * XW * 4, s))) return err;
+  if (nchunks > 1 && (err = d_tmp.alloc((size_t)n_buckets * XW * 4, s))) return err;
   void* d_res;
   if ((err = stage_out(d_res, results, (size_t)PW * 4, cfg->are_results_on_device, s, s_res))) return err;
-  cudaEvent_t ready, copied[2], consumed[2];
+  cudaEvent_t ready, copied[MAX_CHUNKS];
   cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
-  for (int b = 0; b < 2; b++) {
-    cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming);
-  }
+  for (uint32_t i = 0; i < nchunks; i++) cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
   cudaEventRecord(ready, s); // staging buffers exist (stream-ordered allocation) and earlier work on s is ordered before the copies
   cudaStreamWaitEvent(cs, ready, 0);
+  for (uint32_t i = 0; i < nchunks; i++) {
+    const uint32_t off = i * chunk;
+    const uint32_t cn = (n - off < chunk) ? (n - off) : chunk;
+    cudaMemcpyAsync(d_s.as<uint8_t>() + (size_t)off * S::BYTES, (const uint8_t*)scalars + (size_t)off * S::BYTES, (size_t)cn * S::BYTES,
+                    cudaMemcpyHostToDevice, cs);
+    cudaMemcpyAsync(d_p.as<uint8_t>() + (size_t)off * pf * AW * 4, (const uint8_t*)bases + (size_t)off * pf * AW * 4, (size_t)cn * pf * AW * 4,
+                    cudaMemcpyHostToDevice, cs);
+    cudaEventRecord(copied[i], cs);
+  }
   StageTimer prof;
   prof.begin(s);
   int rc = B200_SUCCESS;
   for (uint32_t i = 0; i < nchunks && rc == B200_SUCCESS; i++) {
-    const int b = i & 1;
     const uint32_t off = i * chunk;
     const uint32_t cn = (n - off < chunk) ? (n - off) : chunk;
-    if (i >= 2) cudaStreamWaitEvent(cs, consumed[b], 0);
-    cudaMemcpyAsync(d_s[b].p, (const uint8_t*)scalars + (size_t)off * S::BYTES, (size_t)cn * S::BYTES, cudaMemcpyHostToDevice, cs);
-    cudaMemcpyAsync(d_p[b].p, (const uint8_t*)bases + (size_t)off * pf * AW * 4, (size_t)cn * pf * AW * 4, cudaMemcpyHostToDevice, cs);
-    cudaEventRecord(copied[b], cs);
-    cudaStreamWaitEvent(s, copied[b], 0);
+    cudaStreamWaitEvent(s, copied[i], 0);
+    uint32_t* cp = d_p.as<uint32_t>() + (size_t)off * pf * AW;
     if (!cfg->are_points_montgomery_form) {
       const uint64_t ncoord = (uint64_t)cn * pf * 2 * (F::N / B::N);
       unsigned g = (unsigned)std::min<uint64_t>((ncoord + 255) / 256, (uint64_t)num_sms() * 16);
-      k_to_mont<B><<<g, 256, 0, s>>>(d_p[b].as<uint32_t>(), d_p[b].as<uint32_t>(), ncoord); B200_LAUNCHED(1);
+      k_to_mont<B><<<g, 256, 0, s>>>(cp, cp, ncoord); B200_LAUNCHED(1);
     }
-    b200_msm_config sub = *cfg;
-    sub.batch_size = 1;
-    const MsmPlan pl = make_plan<C>((int)cn, &sub);
-    rc = msm_core<C>(d_s[b].p, d_p[b].as<uint32_t>(), cn, pl, 1, true, &sub, d_part.as<uint32_t>() + (size_t)i * PW, s, prof);
-    cudaEventRecord(consumed[b], s);
+    uint32_t* target = (i == 0) ? d_bkt.as<uint32_t>() : d_tmp.as<uint32_t>();
+    rc = msm_core<C>(d_s.as<uint8_t>() + (size_t)off * S::BYTES, cp, cn, pl, 1, true, &sub, nullptr, s, prof, target, MSM_ACC);
+    if (rc == B200_SUCCESS && i > 0) {
+      k_bucket_merge<F><<<(unsigned)((n_buckets + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(d_bkt.as<uint32_t>(), d_tmp.as<uint32_t>(), n_buckets);
+      B200_LAUNCHED(1);
+      if (cudaGetLastError() != cudaSuccess) rc = B200_UNKNOWN_ERROR;
+      prof.mark("merge");
+    }
   }
-  if (rc == B200_SUCCESS) {
-    k_proj_sum<F><<<1, 32, 0, s>>>(d_part.as<uint32_t>(), nchunks, (uint32_t*)d_res); B200_LAUNCHED(1);
-    if (cudaGetLastError() != cudaSuccess) rc = B200_UNKNOWN_ERROR;
-  }
+  if (rc == B200_SUCCESS) rc = msm_core<C>(nullptr, nullptr, chunk, pl, 1, true, &sub, d_res, s, prof, d_bkt.as<uint32_t>(), MSM_RED);
   prof.mark("final");
   prof.finish("msm_pipelined");
   if (rc == B200_SUCCESS) rc = finish_out(results, d_res, (size_t)PW * 4, cfg->are_results_on_device, cfg->is_async, s);
@@ -789,10 +841,7 @@ int msm_pipelined(const void* scalars, const void* bases, uint32_t n, const b200
     cudaStreamSynchronize(s);
   }
   cudaEventDestroy(ready);
-  for (int b = 0; b < 2; b++) {
-    cudaEventDestroy(copied[b]);
-    cudaEventDestroy(consumed[b]);
-  }
+  for (uint32_t i = 0; i < nchunks; i++) cudaEventDestroy(copied[i]);
   return rc;
 }
 
@@ -806,7 +855,7 @@ int msm_impl(const void* scalars, const void* bases, int msm_size, const b200_ms
   cudaStream_t s = (cudaStream_t)cfg->stream;
   const int batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
   if (msm_size <= 0) return B200_INVALID_ARGUMENT;
-  if (batch == 1 && !cfg->are_scalars_on_device && !cfg->are_points_on_device && (uint32_t)msm_size >= (1u << 23) &&
+  if (batch == 1 && !cfg->are_scalars_on_device && !cfg->are_points_on_device && (uint32_t)msm_size >= pipeline_min_points() &&
       (uint64_t)msm_size * (cfg->precompute_factor > 0 ? cfg->precompute_factor : 1) < (1ull << 31) && !getenv("B200_MSM_NO_PIPELINE"))
     return msm_pipelined<C>(scalars, bases, (uint32_t)msm_size, cfg, results);
   const MsmPlan pl = make_plan<C>(msm_size, cfg);

@@ -1,6 +1,8 @@
 // One translation unit per curve group (compiled with -DB200_MSM_CURVE=<b200_curve_t value>) so the heavy templates
 // build in parallel.  The entry points are looked up by icicle_b200/csrc/msm.cu.
 #include "msm_impl.cuh"
+#include <type_traits>
+#include "ecntt.cuh"
 
 #define B200_CAT2(a, b) a##b
 #define B200_CAT(a, b) B200_CAT2(a, b)
@@ -23,6 +25,19 @@ using namespace b200;
 using namespace b200::msm;
 typedef CurveOf<B200_MSM_CURVE>::type ThisCurve;
 
+// the reference registers ECNTT for G1 only (ecntt_backend.h:15-22: projective_t); the Fq2 curves do not instantiate it
+template <class C, bool G1 = std::is_same<typename C::Base, typename base_fp<typename C::Base>::type>::value>
+struct EcnttEntry {
+  static int run(const void* in, int size, int dir, const b200_ntt_config* cfg, void* out, const uint32_t* tw, const uint32_t* aux, int dom_log)
+  {
+    return ecntt::ecntt_impl<C>(in, size, dir, cfg, out, tw, aux, dom_log);
+  }
+};
+template <class C>
+struct EcnttEntry<C, false> {
+  static int run(const void*, int, int, const b200_ntt_config*, void*, const uint32_t*, const uint32_t*, int) { return B200_API_NOT_IMPLEMENTED; }
+};
+
 extern "C" {
 __attribute__((visibility("hidden"))) int B200_CAT(b200_msm_entry_, B200_MSM_CURVE)(
   const void* scalars, const void* bases, int msm_size, const b200_msm_config* cfg, void* results)
@@ -38,6 +53,11 @@ __attribute__((visibility("hidden"))) int B200_CAT(b200_ec_sum_entry_, B200_MSM_
   const void* points, int n, const b200_vec_ops_config* cfg, void* out)
 {
   return ec_sum_impl<ThisCurve>(points, n, cfg, out);
+}
+__attribute__((visibility("hidden"))) int B200_CAT(b200_ecntt_entry_, B200_MSM_CURVE)(
+  const void* input, int size, int dir, const b200_ntt_config* cfg, void* output, const uint32_t* tw, const uint32_t* aux, int dom_log)
+{
+  return EcnttEntry<ThisCurve>::run(input, size, dir, cfg, output, tw, aux, dom_log);
 }
 __attribute__((visibility("hidden"))) int B200_CAT(b200_msm_plan_c_entry_, B200_MSM_CURVE)(int msm_size, const b200_msm_config* cfg)
 {

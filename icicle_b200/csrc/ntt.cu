@@ -895,6 +895,89 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
   return finish_out(output, dout, bytes, cfg->are_outputs_on_device, cfg->is_async, s);
 }
 
+// ---- extension-field NTT (quartic extension of a 4-byte field) -----------------------------------------------------------
+// The reference's extension NTT (NttExtFieldImpl, icicle/include/icicle/backend/ntt_backend.h:32-48; CPU: cpu_ntt<scalar_t,
+// extension_t>, icicle/backend/cpu/src/field/cpu_ntt.cpp) multiplies extension elements by BASE-field twiddles, which is
+// coefficient-wise, so an NTT of N quartic elements is 4 independent base-field NTTs over the interleaved coefficients.
+// The planes are split out (one 16-byte load per element, four coalesced 4-byte stores), run through the fast row-batched
+// 32-column pass (ntt31.cuh) as a batch of 4*batch transforms, and interleaved back; two extra streaming passes instead of
+// the strided (columns_batch) schedule.
+__global__ void __launch_bounds__(256) k_ext4_split(const uint4* __restrict__ in, uint32_t* __restrict__ out, uint64_t m)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 v = in[i];
+    out[i] = v.x;
+    out[m + i] = v.y;
+    out[2 * m + i] = v.z;
+    out[3 * m + i] = v.w;
+  }
+}
+__global__ void __launch_bounds__(256) k_ext4_join(const uint32_t* __restrict__ in, uint4* __restrict__ out, uint64_t m)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = make_uint4(in[i], in[m + i], in[2 * m + i], in[3 * m + i]);
+}
+// generic 32x32-tile transpose of 4-byte words (columns_batch layouts): out[c*rows + r] = in[r*cols + c]
+__global__ void __launch_bounds__(256) k_transpose_w(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t rows, uint64_t cols)
+{
+  __shared__ uint32_t tile[32][33];
+  const uint64_t bx = (uint64_t)blockIdx.x * 32, by = (uint64_t)blockIdx.y * 32;
+  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (uint32_t j = ty; j < 32; j += 8) {
+    const uint64_t r = by + j, c = bx + tx;
+    if (r < rows && c < cols) tile[j][tx] = in[r * cols + c];
+  }
+  __syncthreads();
+  for (uint32_t j = ty; j < 32; j += 8) {
+    const uint64_t c = bx + j, r = by + tx;
+    if (r < rows && c < cols) out[c * rows + r] = tile[tx][j];
+  }
+}
+
+template <class F>
+int ntt_ext4_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output)
+{
+  static_assert(F::N == 1, "quartic extension NTT is provided for the 4-byte fields");
+  constexpr int DEG = 4;
+  cudaStream_t s = (cudaStream_t)cfg->stream;
+  if (size <= 0 || (size & (size - 1))) return B200_INVALID_ARGUMENT;
+  const uint32_t batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
+  const uint64_t m = (uint64_t)size * batch; // extension elements
+  const size_t bytes = m * DEG * F::BYTES;
+  if ((uint64_t)batch * DEG > 0x7fffffffull) return B200_INVALID_ARGUMENT;
+  Scratch sin, sout, sa, sb;
+  const void* din;
+  void* dout;
+  int err;
+  if ((err = stage_in(din, input, bytes, cfg->are_inputs_on_device, s, sin))) return err;
+  if ((err = stage_out(dout, output, bytes, cfg->are_outputs_on_device, s, sout))) return err;
+  if ((err = sa.alloc(bytes, s))) return err;
+  if ((err = sb.alloc(bytes, s))) return err;
+  const unsigned g = (unsigned)std::min<uint64_t>((m + 255) / 256, (uint64_t)num_sms() * 32);
+  if (!cfg->columns_batch) {
+    k_ext4_split<<<g, 256, 0, s>>>((const uint4*)din, sa.as<uint32_t>(), m); B200_LAUNCHED(1);
+  } else { // [size][batch*4] words -> [batch*4][size]
+    dim3 grid((unsigned)(((uint64_t)batch * DEG + 31) / 32), (unsigned)((size + 31) / 32));
+    k_transpose_w<<<grid, 256, 0, s>>>((const uint32_t*)din, sa.as<uint32_t>(), (uint64_t)size, (uint64_t)batch * DEG); B200_LAUNCHED(1);
+  }
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  b200_ntt_config sub = *cfg;
+  sub.batch_size = (int)(batch * DEG);
+  sub.columns_batch = 0;
+  sub.are_inputs_on_device = 1;
+  sub.are_outputs_on_device = 1;
+  sub.is_async = 1;
+  if ((err = ntt_impl<F>(d, sa.p, size, dir, &sub, sb.p))) return err;
+  if (!cfg->columns_batch) {
+    k_ext4_join<<<g, 256, 0, s>>>(sb.as<uint32_t>(), (uint4*)dout, m); B200_LAUNCHED(1);
+  } else {
+    dim3 grid((unsigned)((size + 31) / 32), (unsigned)(((uint64_t)batch * DEG + 31) / 32));
+    k_transpose_w<<<grid, 256, 0, s>>>(sb.as<uint32_t>(), (uint32_t*)dout, (uint64_t)batch * DEG, (uint64_t)size); B200_LAUNCHED(1);
+  }
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  return finish_out(output, dout, bytes, cfg->are_outputs_on_device, cfg->is_async, s);
+}
+
 } // namespace
 
 extern "C" {
@@ -957,6 +1040,32 @@ int b200_ntt_get_root_of_unity_from_domain(int field, uint64_t logn, void* rou_o
     return b200_convert_montgomery(field, host_m, 1, 0, &vc, rou_out);
   });
   return B200_API_NOT_IMPLEMENTED;
+}
+
+// internal (not part of the C ABI): the device tables of a field's NTT domain for the ECNTT (msm.cu / ecntt.cuh); *tw stays
+// NULL when no domain is initialised on the current device
+__attribute__((visibility("hidden"))) int b200_internal_ntt_domain(int field, const uint32_t** tw, const uint32_t** aux, int* max_log)
+{
+  if (field < 0 || field >= B200_FIELD_COUNT) return B200_INVALID_ARGUMENT;
+  Domain* d;
+  int err = get_domain(field, &d);
+  if (err) return err;
+  std::lock_guard<std::mutex> lock(d->mu);
+  *tw = d->valid ? d->twiddles : nullptr;
+  *aux = d->valid ? d->aux : nullptr;
+  *max_log = d->valid ? d->max_log : 0;
+  return B200_SUCCESS;
+}
+
+int b200_ntt_extension(int field, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output)
+{
+  if (!cfg || !input || !output) return B200_INVALID_POINTER;
+  if (field != B200_FIELD_BABYBEAR && field != B200_FIELD_KOALABEAR) return B200_API_NOT_IMPLEMENTED; // quartic extensions (babybear.h:88-93, koalabear.h:88-93)
+  Domain* d;
+  int err = get_domain(field, &d);
+  if (err) return err;
+  if (field == B200_FIELD_BABYBEAR) return ntt_ext4_impl<Fp<params::babybear>>(d, input, size, dir, cfg, output);
+  return ntt_ext4_impl<Fp<params::koalabear>>(d, input, size, dir, cfg, output);
 }
 
 int b200_ntt(int field, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output)

@@ -1,7 +1,8 @@
 // libicicle_backend_cuda_curve_<curve>.so : MSM (+G2), precompute-bases and curve Montgomery-conversion registrations.
 // Hooks used: REGISTER_MSM_BACKEND / REGISTER_MSM_PRE_COMPUTE_BASES_BACKEND / REGISTER_MSM_G2_BACKEND /
 // REGISTER_MSM_G2_PRE_COMPUTE_BASES_BACKEND (icicle/include/icicle/backend/msm_backend.h:21,38,57,74) and
-// REGISTER_{AFFINE,PROJECTIVE}[_G2]_CONVERT_MONTGOMERY_BACKEND (icicle/include/icicle/curves/montgomery_conversion.h:27,45,...).
+// REGISTER_{AFFINE,PROJECTIVE}[_G2]_CONVERT_MONTGOMERY_BACKEND (icicle/include/icicle/curves/montgomery_conversion.h:27,45,...),
+// REGISTER_ECNTT_BACKEND (icicle/include/icicle/backend/ecntt_backend.h:26-33) on curves whose scalar field has an NTT.
 #include "shim_common.h"
 #include "icicle/msm.h"
 #include "icicle/vec_ops.h"
@@ -9,6 +10,11 @@
 #include "icicle/backend/msm_config.h"
 #include "icicle/curves/curve_config.h"
 #include "icicle/curves/montgomery_conversion.h"
+#ifdef ECNTT
+  #include "icicle/ntt.h"
+  #include "icicle/backend/ntt_config.h"
+  #include "icicle/backend/ecntt_backend.h"
+#endif
 
 using namespace icicle;
 using namespace curve_config;
@@ -75,6 +81,25 @@ namespace {
     return to_err(b200_projective_convert_montgomery(CURVE, in, n, is_into, &c, out));
   }
 
+#ifdef ECNTT
+  // ECNttFieldImpl (ecntt_backend.h:15-22): projective_t elements, scalar_t twiddles from the scalar field's NTT domain
+  template <int CURVE>
+  eIcicleError ecntt_t(const Device&, const projective_t* in, int size, NTTDir dir, const NTTConfig<scalar_t>& config, projective_t* out)
+  {
+    b200_ntt_config c;
+    b200_ntt_default_config(&c);
+    c.stream = config.stream;
+    c.coset_gen = &config.coset_gen;
+    c.batch_size = config.batch_size;
+    c.columns_batch = config.columns_batch;
+    c.are_inputs_on_device = config.are_inputs_on_device;
+    c.are_outputs_on_device = config.are_outputs_on_device;
+    c.is_async = config.is_async;
+    c.ordering = static_cast<int>(config.ordering);
+    return to_err(b200_ecntt(CURVE, in, size, dir == NTTDir::kForward ? B200_NTT_FORWARD : B200_NTT_INVERSE, &c, out));
+  }
+#endif
+
   constexpr int G1 = g1_curve_id();
   static_assert(G1 >= 0, "this curve has no B200 backend");
 
@@ -84,6 +109,9 @@ REGISTER_MSM_BACKEND(B200_DEVICE_TYPE, (msm_t<G1, affine_t, projective_t>));
 REGISTER_MSM_PRE_COMPUTE_BASES_BACKEND(B200_DEVICE_TYPE, (precompute_t<G1, affine_t>));
 REGISTER_AFFINE_CONVERT_MONTGOMERY_BACKEND(B200_DEVICE_TYPE, (affine_mont_t<G1, affine_t>));
 REGISTER_PROJECTIVE_CONVERT_MONTGOMERY_BACKEND(B200_DEVICE_TYPE, (projective_mont_t<G1, projective_t>));
+#ifdef ECNTT
+REGISTER_ECNTT_BACKEND(B200_DEVICE_TYPE, (ecntt_t<G1>));
+#endif
 #ifdef G2_ENABLED
 REGISTER_MSM_G2_BACKEND(B200_DEVICE_TYPE, (msm_t<G1 + 1, g2_affine_t, g2_projective_t>));
 REGISTER_MSM_G2_PRE_COMPUTE_BASES_BACKEND(B200_DEVICE_TYPE, (precompute_t<G1 + 1, g2_affine_t>));

@@ -1,6 +1,6 @@
 // libicicle_backend_cuda_field_<field>.so : NTT + vec-ops registrations for one scalar field.
 // Hooks used (icicle/include/icicle/backend/ntt_backend.h:23,57,72,85; vec_ops_backend.h:87-226):
-//   REGISTER_NTT_BACKEND, REGISTER_NTT_INIT_DOMAIN_BACKEND, REGISTER_NTT_RELEASE_DOMAIN_BACKEND,
+//   REGISTER_NTT_BACKEND, REGISTER_NTT_EXT_FIELD_BACKEND (EXT_FIELD builds), REGISTER_NTT_INIT_DOMAIN_BACKEND, REGISTER_NTT_RELEASE_DOMAIN_BACKEND,
 //   REGISTER_NTT_GET_ROU_FROM_DOMAIN_BACKEND, REGISTER_VECTOR_{ADD,ACCUMULATE,SUB,MUL}_BACKEND,
 //   REGISTER_SCALAR_{MUL,ADD,SUB}_VEC_BACKEND, REGISTER_VECTOR_{INV,DIV,SUM,PRODUCT}_BACKEND, REGISTER_CONVERT_MONTGOMERY_BACKEND, REGISTER_BIT_REVERSE_BACKEND,
 //   REGISTER_SLICE_BACKEND, REGISTER_MATRIX_TRANSPOSE_BACKEND.
@@ -112,7 +112,7 @@ namespace {
   }
 
 #ifdef NTT
-  eIcicleError ntt_impl(const Device&, const scalar_t* in, int size, NTTDir dir, const NTTConfig<scalar_t>& config, scalar_t* out)
+  b200_ntt_config to_c(const NTTConfig<scalar_t>& config)
   {
     b200_ntt_config c;
     b200_ntt_default_config(&c);
@@ -126,8 +126,22 @@ namespace {
     c.ordering = static_cast<int>(config.ordering);
     c.ext_ntt_algorithm = ext_int(config.ext, CudaBackendConfig::CUDA_NTT_ALGORITHM, 0);
     c.ext_fast_twiddles = ext_int(config.ext, CudaBackendConfig::CUDA_NTT_FAST_TWIDDLES_MODE, 0);
+    return c;
+  }
+  eIcicleError ntt_impl(const Device&, const scalar_t* in, int size, NTTDir dir, const NTTConfig<scalar_t>& config, scalar_t* out)
+  {
+    b200_ntt_config c = to_c(config);
     return to_err(b200_ntt(FIELD, in, size, dir == NTTDir::kForward ? B200_NTT_FORWARD : B200_NTT_INVERSE, &c, out));
   }
+  #ifdef EXT_FIELD
+  // NttExtFieldImpl (ntt_backend.h:32-48): extension_t elements, scalar_t twiddles / coset generator / domain
+  eIcicleError ntt_ext_impl(const Device&, const extension_t* in, int size, NTTDir dir, const NTTConfig<scalar_t>& config, extension_t* out)
+  {
+    static_assert(sizeof(extension_t) == 4 * sizeof(scalar_t), "b200_ntt_extension implements the quartic extension");
+    b200_ntt_config c = to_c(config);
+    return to_err(b200_ntt_extension(FIELD, in, size, dir == NTTDir::kForward ? B200_NTT_FORWARD : B200_NTT_INVERSE, &c, out));
+  }
+  #endif
   eIcicleError ntt_init(const Device&, const scalar_t& root, const NTTInitDomainConfig& config)
   {
     return to_err(b200_ntt_init_domain(FIELD, &root, config.stream));
@@ -161,6 +175,9 @@ REGISTER_SLICE_BACKEND(B200_DEVICE_TYPE, slice_op);
 REGISTER_MATRIX_TRANSPOSE_BACKEND(B200_DEVICE_TYPE, transpose);
 #ifdef NTT
 REGISTER_NTT_BACKEND(B200_DEVICE_TYPE, ntt_impl);
+  #ifdef EXT_FIELD
+REGISTER_NTT_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ntt_ext_impl);
+  #endif
 REGISTER_NTT_INIT_DOMAIN_BACKEND(B200_DEVICE_TYPE, ntt_init);
 REGISTER_NTT_RELEASE_DOMAIN_BACKEND(B200_DEVICE_TYPE, ntt_release);
 REGISTER_NTT_GET_ROU_FROM_DOMAIN_BACKEND(B200_DEVICE_TYPE, ntt_rou);

@@ -172,6 +172,18 @@ B200_API int b200_ntt_init_domain(int field, const void* primitive_root, void* s
 B200_API int b200_ntt_release_domain(int field);
 B200_API int b200_ntt_get_root_of_unity_from_domain(int field, uint64_t logn, void* rou_out);
 B200_API int b200_ntt(int field, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output);
+/* Extension-field NTT -- replaces NttExtFieldImpl (icicle/include/icicle/backend/ntt_backend.h:32-48, dispatcher
+ * icicle/src/ntt.cpp:86-103; CPU: cpu_ntt<scalar_t, extension_t>, icicle/backend/cpu/src/field/cpu_ntt.cpp): `size` quartic
+ * extension elements (4 base-field coefficients each, 16 B) per transform, BASE-field twiddles / coset generator / domain
+ * (the scalar domain is reused); batch_size, columns_batch, ordering as for b200_ntt.  BabyBear and KoalaBear. */
+B200_API int b200_ntt_extension(int field, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output);
+/* ECNTT -- replaces ECNttFieldImpl (icicle/include/icicle/backend/ecntt_backend.h:15-22, frontend icicle/src/ecntt.cpp:5-18;
+ * CPU: ntt_cpu::cpu_ntt<scalar_t, projective_t>, icicle/backend/cpu/src/curve/cpu_ecntt.cpp:12-19): the NTT of `size` G1
+ * points (homogeneous projective, standard form, 3*|Fq| bytes each) with the curve's SCALAR-field twiddles, i.e.
+ * out[k] = sum_i w^(ik) * (g^i * P_i); the scalar field's domain must have been initialised with b200_ntt_init_domain.
+ * `curve` is a G1 b200_curve_t of bn254 / bls12_381 / bls12_377 / bw6_761 (the reference's ECNTT feature list,
+ * icicle/cmake/features.cmake:15-18).  Results are the reference's group elements (not its representatives). */
+B200_API int b200_ecntt(int curve, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * vec-ops around the path -- replace the per-op hooks of icicle/include/icicle/backend/vec_ops_backend.h:11-83,85-270,

@@ -232,6 +232,22 @@ class Ref:
         _chk(self._f(self.field, "ntt")(self._p(inp), C.c_int(size), C.c_int(direction), C.byref(cfg), self._p(out)), "ntt")
         return out
 
+    def ecntt(self, inp, size, direction, coset_gen=None, **cfgkw):
+        """<curve>_ecntt (icicle/src/ecntt.cpp:8-12): NTT over G1 projective points with scalar-field twiddles."""
+        cfg = self.ntt_config(coset_gen, **cfgkw)
+        inp = np.ascontiguousarray(inp, dtype=np.uint32)
+        out = np.zeros_like(inp)
+        _chk(self._f(self.curve, "ecntt")(self._p(inp), C.c_int(size), C.c_int(direction), C.byref(cfg), self._p(out)), "ecntt")
+        return out
+
+    def extension_ntt(self, inp, size, direction, coset_gen=None, **cfgkw):
+        """<field>_extension_ntt (icicle/src/ntt.cpp:90-95): elements are quartic extension elements (4 base limbs rows)."""
+        cfg = self.ntt_config(coset_gen, **cfgkw)
+        inp = np.ascontiguousarray(inp, dtype=np.uint32)
+        out = np.zeros_like(inp)
+        _chk(self._f(self.field, "extension_ntt")(self._p(inp), C.c_int(size), C.c_int(direction), C.byref(cfg), self._p(out)), "extension_ntt")
+        return out
+
     # ---- vec ops ---------------------------------------------------------------------------------------------------------
     def vec2(self, op, a, b, size, **cfgkw):
         cfg = self.vec_config(**cfgkw)

@@ -106,3 +106,16 @@ def ntt_naive_ints(x, w, p, inverse=False, coset=1):
     ninv = pow(n, -1, p)
     gi = pow(coset, -1, p)
     return [ninv * pow(gi, i, p) * sum(x[k] * pow(wi, i * k, p) for k in range(n)) % p for i in range(n)]
+
+
+def affine_to_projective_limbs(aff, limbs):
+    """(n, 2*limbs) affine points -> (n, 3*limbs) homogeneous projective (x, y, 1); affine zero (0,0) -> (0, 1, 0)
+    (icicle/include/icicle/curves/projective.h:26-31)."""
+    aff = np.asarray(aff, dtype=np.uint32).reshape(-1, 2 * limbs)
+    out = np.zeros((aff.shape[0], 3 * limbs), dtype=np.uint32)
+    out[:, : 2 * limbs] = aff
+    out[:, 2 * limbs] = 1
+    zero = ~aff.any(axis=1)
+    out[zero, 2 * limbs] = 0
+    out[zero, limbs] = 1
+    return out

@@ -178,3 +178,31 @@ def test_polynomial_api_on_device(r):
         assert exp[k][0] == got[k][0], k
         assert np.array_equal(exp[k][1], got[k][1]), k
     r.set_device("CPU", 0)
+
+
+def test_ecntt_main_vs_ref_device(r):
+    """`bn254_ecntt` through the unmodified frontend: REGISTER_ECNTT_BACKEND("CUDA", ...) in our curve DSO vs the CPU device
+    (icicle/tests/test_curve_api.cpp:293-400 compares the same way, as group elements)."""
+    import common
+    if not hasattr(r.curve, "bn254_ecntt"):
+        pytest.skip("reference built without ECNTT")
+    logn = 6
+    n = 1 << logn
+    r.set_device("CPU", 0)
+    root = r.get_root_of_unity(1 << (logn + 1))
+    r.ntt_init_domain(root)
+    P = common.affine_to_projective_limbs(r.generate_affine_points(n), 8)
+    r.set_device("CUDA", 0)
+    r.ntt_init_domain(root)
+    for direction in (0, 1):
+        for ordering in (0, 1, 2):
+            r.set_device("CPU", 0)
+            exp = r.ecntt(P, n, direction, ordering=ordering)
+            r.set_device("CUDA", 0)
+            got = r.ecntt(P, n, direction, ordering=ordering)
+            for i in range(n):
+                assert r.projective_eq(got[i], exp[i]), (direction, ordering, i)
+    r.set_device("CUDA", 0)
+    r.ntt_release_domain()
+    r.set_device("CPU", 0)
+    r.ntt_release_domain()

@@ -108,3 +108,40 @@ def test_small_field_ntt_big_golden(name, field):
                 if "out_" + key in g.files:
                     assert np.array_equal(y, g["out_" + key]), key
     ib.ntt_release_domain(field)
+
+
+@pytest.mark.parametrize("name,field", [("babybear", ib.Field.BABYBEAR), ("koalabear", ib.Field.KOALABEAR)])
+def test_extension_ntt_golden(name, field):
+    """Quartic-extension NTT (b200_ntt_extension) vs outputs of the unmodified reference CPU backend built with EXT_FIELD
+    (`<field>_extension_ntt`; tests/golden/<field>_ext_ntt.npz, tools/make_golden_ext.py): forward / inverse, coset, row and
+    columns batches, kNN and kNR, sizes 1 .. 2^16; bit-exact (full arrays or SHA-256 of the bytes)."""
+    import hashlib
+    g = np.load(os.path.join(GOLD, f"{name}_ext_ntt.npz"))
+    p = utils.field_params(name)["p"]
+    ib.ntt_release_domain(field)
+    ib.ntt_init_domain(field, g["ntt_root"].reshape(-1))
+    for logn, batch, col, ordering in g["cases"].tolist():
+        rs = np.random.RandomState(4000 + logn)
+        x = rs.randint(0, p, size=(batch << logn, 4), dtype=np.int64).astype(np.uint32)
+        for d in (0, 1):
+            for c in (0, 1):
+                cfg = ib.NTTConfig(batch_size=batch, columns_batch=bool(col), ordering=ib.Ordering(ordering),
+                                   coset_gen=g["coset_arb"].reshape(-1) if c else None)
+                y = ib.ntt_extension(field, x, 1 << logn, d, cfg)
+                key = f"l{logn}_b{batch}_c{col}_o{ordering}_d{d}_g{c}"
+                if "out_" + key in g.files:
+                    assert np.array_equal(y, g["out_" + key]), key
+                assert hashlib.sha256(np.ascontiguousarray(y, dtype=np.uint32).tobytes()).digest() == g["sha_" + key].tobytes(), key
+    # device-resident, in place, round trip at a size the tile pass handles in 2 passes
+    n = 1 << 15
+    rs = np.random.RandomState(77)
+    x = rs.randint(0, p, size=(n * 2, 4), dtype=np.int64).astype(np.uint32)
+    dx = ib.to_device(x)
+    ib.ntt_extension(field, dx, n, 0, ib.NTTConfig(batch_size=2, are_outputs_on_device=True), dx)
+    # coefficient planes: the extension transform is 4 base-field transforms over the interleaved coefficients
+    planes = np.ascontiguousarray(x.reshape(2, n, 4).transpose(0, 2, 1)).reshape(-1, 1)    # [batch][4][n]
+    yb = ib.ntt(field, planes, n, 0, ib.NTTConfig(batch_size=8))
+    assert np.array_equal(ib.to_host(dx).reshape(2, n, 4), yb.reshape(2, 4, n).transpose(0, 2, 1))
+    ib.ntt_extension(field, dx, n, 1, ib.NTTConfig(batch_size=2, are_outputs_on_device=True), dx)
+    assert np.array_equal(ib.to_host(dx).reshape(-1, 4), x)
+    ib.ntt_release_domain(field)

@@ -225,6 +225,42 @@ def test_pipelined_host_path_matches_device_path():
     assert common.projective_to_affine_ints(host, 8, q) == common.projective_to_affine_ints(dev, 8, q)
 
 
+def test_pipelined_host_path_vs_reference_small(ref, monkeypatch):
+    """The host-pointer pipeline (chunked H2D on a copy stream, per-chunk accumulation into one shared bucket array with the
+    window size of the whole MSM, k_bucket_merge, one bucket reduction) forced at small sizes: same group element as the
+    reference CPU backend for ragged chunk splits, chunk counts 1..7, forced pair levels and the degenerate inputs."""
+    C = ib.Curve.BN254_G1
+    monkeypatch.setenv("B200_MSM_PIPELINE_MIN", "2")
+    for n, chunks in ((2, 2), (3, 2), (1000, 3), ((1 << 12) + 17, 7), (1 << 13, 1), ((1 << 14) - 1, 5)):
+        monkeypatch.setenv("B200_MSM_PIPELINE_CHUNKS", str(chunks))
+        s = ref.generate_scalars(n)
+        P = ref.generate_affine_points(n)   # 100 distinct points repeated: doublings inside buckets, across chunks too
+        exp = ref.msm(s, P, n)
+        for lv, c in ((0, 0), (2, 7), (1, 12), (0, 15)):
+            monkeypatch.setenv("B200_MSM_PAIR_LEVELS", str(lv))
+            got = ib.msm(C, s, P, n, ib.MSMConfig(c=c))
+            assert ref.projective_eq(got[0], exp[0]), (n, chunks, lv, c)
+    # bitsize=1 (one huge bucket), zero bases, Montgomery-form scalars, P + (-P) in different chunks
+    monkeypatch.setenv("B200_MSM_PIPELINE_CHUNKS", "4")
+    monkeypatch.setenv("B200_MSM_PAIR_LEVELS", "1")
+    n = 1 << 12
+    s = ref.generate_scalars(n)
+    P = ref.generate_affine_points(n)
+    P[5] = 0
+    P[n - 1] = 0
+    assert ref.projective_eq(ib.msm(C, s, P, n, ib.MSMConfig(bitsize=1))[0], ref.msm(s, P, n, bitsize=1)[0])
+    q = utils.field_params("bn254_fq")["p"]
+    P2 = common.gen_g1_points("bn254", n, 5)
+    half = n // 2
+    P2[half:] = P2[:half]
+    yi = utils.from_limbs(P2[half:, 8:])
+    P2[half:, 8:] = utils.to_limbs([(q - y) % q for y in yi], 8)
+    s2 = ref.generate_scalars(n)
+    s2[half:] = s2[:half]
+    got = ib.msm(C, s2, P2, n)
+    assert common.is_projective_zero(ref.msm(s2, P2, n)[0], 8) and common.is_projective_zero(got[0], 8)   # P and -P meet only in the merge
+
+
 @pytest.fixture
 def pair_levels_env():
     """B200_MSM_PAIR_LEVELS forces the number of batched-affine pair levels (msm_pairs.cuh) regardless of size."""

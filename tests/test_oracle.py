@@ -172,3 +172,36 @@ def test_port_ntt_small_fields_vs_reference_golden(name):
                 assert hashlib.sha256(y.tobytes()).digest() == g["sha_" + key].tobytes(), key
                 if "out_" + key in g.files:
                     assert np.array_equal(y, g["out_" + key]), key
+
+
+@pytest.mark.parametrize("name", ["babybear", "koalabear"])
+def test_port_extension_ntt_vs_reference_golden(name):
+    """tests/golden/<field>_ext_ntt.npz (tools/make_golden_ext.py, `<field>_extension_ntt` of the unmodified reference CPU
+    backend built with EXT_FIELD): the quartic-extension NTT multiplies by base-field twiddles, i.e. it is the base-field NTT
+    of the C restatement applied to each of the 4 coefficient planes -- row batches, columns batches, kNN and kNR."""
+    import hashlib
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}_ext_ntt.npz"))
+    p = utils.field_params(name)["p"]
+    root, dom_log, coset = int(g["ntt_root"][0]), int(g["dom_log"][0]), int(g["coset_arb"][0])
+    for logn, batch, col, ordering in g["cases"].tolist():
+        if logn > 12:
+            continue
+        n = 1 << logn
+        rs = np.random.RandomState(4000 + logn)
+        x = rs.randint(0, p, size=(batch << logn, 4), dtype=np.int64).astype(np.uint32)
+        # element (i, b) of transform b: row-major batch -> x[b*n + i], columns batch -> x[i*batch + b]
+        X = x.reshape(batch, n, 4) if not col else x.reshape(n, batch, 4).transpose(1, 0, 2)
+        w = pow(root, 1 << (dom_log - logn), p)
+        perm = np.arange(n)
+        if ordering == 1 and logn > 0:   # kNR: output index bit-reversed
+            perm = np.array([int(format(i, f"0{logn}b")[::-1], 2) for i in range(n)])
+        for d in (0, 1):
+            for c in (0, 1):
+                Y = np.zeros_like(X)
+                for b in range(batch):
+                    for k in range(4):
+                        col_out = port.ntt([int(v) for v in X[b, :, k]], w, p, inverse=bool(d), coset=coset if c else 1, field_name=name)
+                        Y[b, :, k] = np.array(col_out, dtype=np.uint32)[perm]
+                y = Y.reshape(-1, 4) if not col else np.ascontiguousarray(Y.transpose(1, 0, 2)).reshape(-1, 4)
+                key = f"l{logn}_b{batch}_c{col}_o{ordering}_d{d}_g{c}"
+                assert hashlib.sha256(np.ascontiguousarray(y).tobytes()).digest() == g["sha_" + key].tobytes(), key
