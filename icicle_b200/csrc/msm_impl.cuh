@@ -761,10 +761,33 @@ inline uint32_t pipeline_min_points()
   return 1u << 23;
 }
 
-inline uint32_t pipeline_chunks()
+// Chunk schedule of the host-pointer pipeline, as point counts.  The copy stream never waits, so chunk k is on the device at
+// (points up to k) / PCIe rate; the compute stream is the slower of the two (~0.44 vs ~0.57 G points/s for BN254 G1), so
+// the exposed transfer is the FIRST chunk only and the cost of splitting is the shorter bucket runs per chunk (fewer
+// batched-affine levels, one k_bucket_merge per chunk).  Hence: two small chunks to start early, then doubling, then
+// quarters -- 1/16, 1/16, 1/8, 1/4, 1/4, 1/4 (measured on B200, profiles/r1_e2e_pipeline.txt).  B200_MSM_PIPELINE_CHUNKS=k
+// forces k equal chunks instead.
+inline uint32_t pipeline_schedule(uint32_t n, uint32_t* sizes, uint32_t max_chunks)
 {
-  uint32_t k = 8;
-  if (const char* ev = getenv("B200_MSM_PIPELINE_CHUNKS")) k = (uint32_t)std::max(1, std::min(32, atoi(ev)));
+  const bool tiny_ok = getenv("B200_MSM_PIPELINE_MIN") != nullptr; // tests: allow tiny chunks
+  const uint32_t min_chunk = tiny_ok ? 1u : (1u << 20);
+  uint32_t k = 0, left = n;
+  if (const char* ev = getenv("B200_MSM_PIPELINE_CHUNKS")) {
+    const uint32_t want = (uint32_t)std::max(1, std::min((int)max_chunks, atoi(ev)));
+    const uint32_t each = std::max<uint32_t>((n + want - 1) / want, min_chunk);
+    while (left > 0 && k < max_chunks) {
+      sizes[k] = (k + 1 == max_chunks) ? left : std::min(each, left);
+      left -= sizes[k++];
+    }
+    return k;
+  }
+  static const uint32_t shift[6] = {4, 4, 3, 2, 2, 2};
+  for (int i = 0; i < 6 && left > 0; i++) {
+    uint32_t want = std::max<uint32_t>(n >> shift[i], min_chunk);
+    if (i == 5 || left < want + min_chunk) want = left; // the last chunk takes the remainder
+    sizes[k] = std::min(want, left);
+    left -= sizes[k++];
+  }
   return k;
 }
 
@@ -783,10 +806,13 @@ int msm_pipelined(const void* scalars, const void* bases, uint32_t n, const b200
   sub.batch_size = 1;
   const MsmPlan pl = make_plan<C>((int)n, &sub); // one window size for all chunks: they share the bucket array
   const uint32_t pf = (uint32_t)pl.pf;
-  uint32_t chunk = (n + pipeline_chunks() - 1) / pipeline_chunks();
-  chunk = std::max<uint32_t>(chunk, getenv("B200_MSM_PIPELINE_MIN") ? 1u : (1u << 20));
-  const uint32_t nchunks = (n + chunk - 1) / chunk;
-  if (nchunks > MAX_CHUNKS) return B200_INVALID_ARGUMENT;
+  uint32_t csize[MAX_CHUNKS], coff[MAX_CHUNKS];
+  const uint32_t nchunks = pipeline_schedule(n, csize, MAX_CHUNKS);
+  uint32_t max_chunk = 0;
+  for (uint32_t i = 0, o = 0; i < nchunks; o += csize[i], i++) {
+    coff[i] = o;
+    max_chunk = std::max(max_chunk, csize[i]);
+  }
   const uint64_t n_buckets = (uint64_t)pl.nbm << (pl.c - 1);
   int err;
   Scratch d_s, d_p, d_bkt, d_tmp, s_res;
@@ -802,8 +828,7 @@ int msm_pipelined(const void* scalars, const void* bases, uint32_t n, const b200
   cudaEventRecord(ready, s); // staging buffers exist (stream-ordered allocation) and earlier work on s is ordered before the copies
   cudaStreamWaitEvent(cs, ready, 0);
   for (uint32_t i = 0; i < nchunks; i++) {
-    const uint32_t off = i * chunk;
-    const uint32_t cn = (n - off < chunk) ? (n - off) : chunk;
+    const uint32_t off = coff[i], cn = csize[i];
     cudaMemcpyAsync(d_s.as<uint8_t>() + (size_t)off * S::BYTES, (const uint8_t*)scalars + (size_t)off * S::BYTES, (size_t)cn * S::BYTES,
                     cudaMemcpyHostToDevice, cs);
     cudaMemcpyAsync(d_p.as<uint8_t>() + (size_t)off * pf * AW * 4, (const uint8_t*)bases + (size_t)off * pf * AW * 4, (size_t)cn * pf * AW * 4,
@@ -814,8 +839,7 @@ int msm_pipelined(const void* scalars, const void* bases, uint32_t n, const b200
   prof.begin(s);
   int rc = B200_SUCCESS;
   for (uint32_t i = 0; i < nchunks && rc == B200_SUCCESS; i++) {
-    const uint32_t off = i * chunk;
-    const uint32_t cn = (n - off < chunk) ? (n - off) : chunk;
+    const uint32_t off = coff[i], cn = csize[i];
     cudaStreamWaitEvent(s, copied[i], 0);
     uint32_t* cp = d_p.as<uint32_t>() + (size_t)off * pf * AW;
     if (!cfg->are_points_montgomery_form) {
@@ -832,7 +856,7 @@ int msm_pipelined(const void* scalars, const void* bases, uint32_t n, const b200
       prof.mark("merge");
     }
   }
-  if (rc == B200_SUCCESS) rc = msm_core<C>(nullptr, nullptr, chunk, pl, 1, true, &sub, d_res, s, prof, d_bkt.as<uint32_t>(), MSM_RED);
+  if (rc == B200_SUCCESS) rc = msm_core<C>(nullptr, nullptr, max_chunk, pl, 1, true, &sub, d_res, s, prof, d_bkt.as<uint32_t>(), MSM_RED);
   prof.mark("final");
   prof.finish("msm_pipelined");
   if (rc == B200_SUCCESS) rc = finish_out(results, d_res, (size_t)PW * 4, cfg->are_results_on_device, cfg->is_async, s);

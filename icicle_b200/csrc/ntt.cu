@@ -703,6 +703,58 @@ int plan_passes(int n_log, int maxr, int* radices)
   return k;
 }
 
+// generic 32x32-tile transpose of 4-byte words (columns_batch layouts): out[c*rows + r] = in[r*cols + c]
+__global__ void __launch_bounds__(256) k_transpose_w(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t rows, uint64_t cols)
+{
+  __shared__ uint32_t tile[32][33];
+  const uint64_t bx = (uint64_t)blockIdx.x * 32, by = (uint64_t)blockIdx.y * 32;
+  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (uint32_t j = ty; j < 32; j += 8) {
+    const uint64_t r = by + j, c = bx + tx;
+    if (r < rows && c < cols) tile[j][tx] = in[r * cols + c];
+  }
+  __syncthreads();
+  for (uint32_t j = ty; j < 32; j += 8) {
+    const uint64_t c = bx + j, r = by + tx;
+    if (r < rows && c < cols) out[c * rows + r] = tile[tx][j];
+  }
+}
+
+
+template <class F>
+int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output);
+
+// columns_batch for the 4-byte fields: a [size][cols] matrix of independent columns (the usual STARK trace layout) is
+// transposed to [cols][size], run through the row-batched 32-column tile pass (ntt31.cuh) and transposed back -- two extra
+// streaming passes (16 B/element) instead of ~7 strided register-only radix-16 passes.  din/dout are device pointers.
+template <class F>
+int ntt_columns_transposed(Domain* d, const void* din, void* dout, int size, uint64_t cols, int dir, const b200_ntt_config* cfg, cudaStream_t s)
+{
+  static_assert(F::N == 1, "word transpose");
+  const size_t bytes = (size_t)size * cols * F::BYTES;
+  Scratch sa;
+  int err;
+  if ((err = sa.alloc(bytes, s))) return err;
+  {
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((size + 31) / 32));
+    k_transpose_w<<<grid, 256, 0, s>>>((const uint32_t*)din, sa.as<uint32_t>(), (uint64_t)size, cols); B200_LAUNCHED(1);
+    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  }
+  b200_ntt_config sub = *cfg;
+  sub.batch_size = (int)cols;
+  sub.columns_batch = 0;
+  sub.are_inputs_on_device = 1;
+  sub.are_outputs_on_device = 1;
+  sub.is_async = 1;
+  if ((err = ntt_impl<F>(d, sa.p, size, dir, &sub, sa.p))) return err;
+  {
+    dim3 grid((unsigned)((size + 31) / 32), (unsigned)((cols + 31) / 32));
+    k_transpose_w<<<grid, 256, 0, s>>>(sa.as<uint32_t>(), (uint32_t*)dout, cols, (uint64_t)size); B200_LAUNCHED(1);
+    B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  }
+  return B200_SUCCESS;
+}
+
 template <class F>
 int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output)
 {
@@ -732,6 +784,14 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
   int err;
   if ((err = stage_in(din, input, bytes, cfg->are_inputs_on_device, s, sin))) return err;
   if ((err = stage_out(dout, output, bytes, cfg->are_outputs_on_device, s, sout))) return err;
+
+  if constexpr (F::N == 1) {
+    if (cfg->columns_batch && batch > 1 && n_log >= 10 && cfg->ext_ntt_algorithm != B200_NTT_ALG_RADIX2 && !getenv("B200_NTT31_OFF") &&
+        !getenv("B200_NTT_COLUMNS_STRIDED")) {
+      if ((err = ntt_columns_transposed<F>(d, din, dout, size, batch, dir, cfg, s))) return err;
+      return finish_out(output, dout, bytes, cfg->are_outputs_on_device, cfg->is_async, s);
+    }
+  }
 
   // ---- coset tables -------------------------------------------------------------------------------------------------
   bool has_coset = false;
@@ -917,23 +977,6 @@ __global__ void __launch_bounds__(256) k_ext4_join(const uint32_t* __restrict__ 
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x)
     out[i] = make_uint4(in[i], in[m + i], in[2 * m + i], in[3 * m + i]);
 }
-// generic 32x32-tile transpose of 4-byte words (columns_batch layouts): out[c*rows + r] = in[r*cols + c]
-__global__ void __launch_bounds__(256) k_transpose_w(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t rows, uint64_t cols)
-{
-  __shared__ uint32_t tile[32][33];
-  const uint64_t bx = (uint64_t)blockIdx.x * 32, by = (uint64_t)blockIdx.y * 32;
-  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (uint32_t j = ty; j < 32; j += 8) {
-    const uint64_t r = by + j, c = bx + tx;
-    if (r < rows && c < cols) tile[j][tx] = in[r * cols + c];
-  }
-  __syncthreads();
-  for (uint32_t j = ty; j < 32; j += 8) {
-    const uint64_t c = bx + j, r = by + tx;
-    if (r < rows && c < cols) out[c * rows + r] = tile[tx][j];
-  }
-}
-
 template <class F>
 int ntt_ext4_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output)
 {
@@ -951,15 +994,14 @@ int ntt_ext4_impl(Domain* d, const void* input, int size, int dir, const b200_nt
   int err;
   if ((err = stage_in(din, input, bytes, cfg->are_inputs_on_device, s, sin))) return err;
   if ((err = stage_out(dout, output, bytes, cfg->are_outputs_on_device, s, sout))) return err;
+  const unsigned g = (unsigned)std::min<uint64_t>((m + 255) / 256, (uint64_t)num_sms() * 32);
+  if (cfg->columns_batch) { // [size][batch*4] words: columns of independent base-field transforms
+    if ((err = ntt_columns_transposed<F>(d, din, dout, size, (uint64_t)batch * DEG, dir, cfg, s))) return err;
+    return finish_out(output, dout, bytes, cfg->are_outputs_on_device, cfg->is_async, s);
+  }
   if ((err = sa.alloc(bytes, s))) return err;
   if ((err = sb.alloc(bytes, s))) return err;
-  const unsigned g = (unsigned)std::min<uint64_t>((m + 255) / 256, (uint64_t)num_sms() * 32);
-  if (!cfg->columns_batch) {
-    k_ext4_split<<<g, 256, 0, s>>>((const uint4*)din, sa.as<uint32_t>(), m); B200_LAUNCHED(1);
-  } else { // [size][batch*4] words -> [batch*4][size]
-    dim3 grid((unsigned)(((uint64_t)batch * DEG + 31) / 32), (unsigned)((size + 31) / 32));
-    k_transpose_w<<<grid, 256, 0, s>>>((const uint32_t*)din, sa.as<uint32_t>(), (uint64_t)size, (uint64_t)batch * DEG); B200_LAUNCHED(1);
-  }
+  k_ext4_split<<<g, 256, 0, s>>>((const uint4*)din, sa.as<uint32_t>(), m); B200_LAUNCHED(1);
   B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
   b200_ntt_config sub = *cfg;
   sub.batch_size = (int)(batch * DEG);
@@ -968,12 +1010,7 @@ int ntt_ext4_impl(Domain* d, const void* input, int size, int dir, const b200_nt
   sub.are_outputs_on_device = 1;
   sub.is_async = 1;
   if ((err = ntt_impl<F>(d, sa.p, size, dir, &sub, sb.p))) return err;
-  if (!cfg->columns_batch) {
-    k_ext4_join<<<g, 256, 0, s>>>(sb.as<uint32_t>(), (uint4*)dout, m); B200_LAUNCHED(1);
-  } else {
-    dim3 grid((unsigned)((size + 31) / 32), (unsigned)(((uint64_t)batch * DEG + 31) / 32));
-    k_transpose_w<<<grid, 256, 0, s>>>(sb.as<uint32_t>(), (uint32_t*)dout, (uint64_t)batch * DEG, (uint64_t)size); B200_LAUNCHED(1);
-  }
+  k_ext4_join<<<g, 256, 0, s>>>(sb.as<uint32_t>(), (uint4*)dout, m); B200_LAUNCHED(1);
   B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
   return finish_out(output, dout, bytes, cfg->are_outputs_on_device, cfg->is_async, s);
 }

@@ -61,7 +61,7 @@ def test_ecntt_bn254_vs_reference(ref):
         exp = ref.ecntt(P, n, 0, batch_size=batch, columns_batch=True)
         dP = ib.to_device(P)
         ib.ecntt(C, dP, n, 0, ib.NTTConfig(batch_size=batch, columns_batch=True, are_outputs_on_device=True), dP)
-        got = ib.to_host(dP)
+        got = ib.to_host(dP).reshape(n * batch, 24)
         for i in range(n * batch):
             assert ref.projective_eq(got[i], exp[i]), i
     finally:
@@ -124,7 +124,7 @@ def test_ecntt_roundtrip_2p10_device():
     aff = common.gen_g1_points("bn254", n, 5)
     dP = ib.to_device(common.affine_to_projective_limbs(aff, 8))
     mid = ib.ecntt(C, dP, n, 0, ib.NTTConfig(are_outputs_on_device=True, ordering=ib.Ordering.kNR))
-    back = ib.to_host(ib.ecntt(C, mid, n, 1, ib.NTTConfig(are_outputs_on_device=True, ordering=ib.Ordering.kRN)))
+    back = ib.to_host(ib.ecntt(C, mid, n, 1, ib.NTTConfig(are_outputs_on_device=True, ordering=ib.Ordering.kRN))).reshape(n, 24)
     exp = common.affine_limbs_to_ints(aff, 8)
     for i in range(0, n, 37):
         assert common.projective_to_affine_ints(back[i], 8, q) == exp[i], i

@@ -240,6 +240,13 @@ def test_pipelined_host_path_vs_reference_small(ref, monkeypatch):
             monkeypatch.setenv("B200_MSM_PAIR_LEVELS", str(lv))
             got = ib.msm(C, s, P, n, ib.MSMConfig(c=c))
             assert ref.projective_eq(got[0], exp[0]), (n, chunks, lv, c)
+    # the default graded schedule (1/16, 1/16, 1/8, 1/4, 1/4, rest)
+    monkeypatch.delenv("B200_MSM_PIPELINE_CHUNKS")
+    monkeypatch.setenv("B200_MSM_PAIR_LEVELS", "2")
+    for n in (5, 100, (1 << 13) + 11):
+        s = ref.generate_scalars(n)
+        P = ref.generate_affine_points(n)
+        assert ref.projective_eq(ib.msm(C, s, P, n, ib.MSMConfig(c=9))[0], ref.msm(s, P, n)[0]), n
     # bitsize=1 (one huge bucket), zero bases, Montgomery-form scalars, P + (-P) in different chunks
     monkeypatch.setenv("B200_MSM_PIPELINE_CHUNKS", "4")
     monkeypatch.setenv("B200_MSM_PAIR_LEVELS", "1")

@@ -196,3 +196,38 @@ def test_small_field_tile_pass(field, name, dom_log):
     ib.ntt(field, y, n, ib.NTTDir.kInverse, ib.NTTConfig(), z)
     assert torch.equal(z.view(torch.int32).view(-1), xd.view(-1))
     ib.ntt_release_domain(field)
+
+
+@pytest.mark.parametrize("field,name", [(ib.Field.BABYBEAR, "babybear"), (ib.Field.KOALABEAR, "koalabear")])
+def test_small_field_columns_batch_transposed_path(field, name):
+    """columns_batch on the 4-byte fields at n >= 2^10 goes transpose -> row-batched tile pass -> transpose
+    (ntt_columns_transposed): bit-identical to (a) the row-batched transform of the transposed data (itself pinned to the
+    reference goldens) and (b) the strided register-only schedule it replaces (B200_NTT_COLUMNS_STRIDED=1), for ragged column
+    counts, every ordering, inverse and coset, host and device buffers, in place."""
+    import os
+    fp = utils.field_params(name)
+    p = fp["p"]
+    dom_log = 14
+    ib.ntt_release_domain(field)
+    ib.ntt_init_domain(field, utils.to_limbs([omega(name, dom_log)], 1)[0])
+    rs = np.random.RandomState(31)
+    g = utils.to_limbs([0x3456789 % p], 1)[0]
+    for logn, cols in ((10, 2), (11, 5), (12, 33), (14, 64)):
+        n = 1 << logn
+        x = rs.randint(0, p, size=(n, cols), dtype=np.int64).astype(np.uint32)        # [n][cols]: column c is one transform
+        xt = np.ascontiguousarray(x.T).reshape(-1, 1)                                  # [cols][n]
+        for d in (ib.NTTDir.kForward, ib.NTTDir.kInverse):
+            for o in (ib.Ordering.kNN, ib.Ordering.kNR, ib.Ordering.kRN, ib.Ordering.kRR):
+                for cg in (None, g):
+                    rows = ib.ntt(field, xt, n, d, ib.NTTConfig(batch_size=cols, ordering=o, coset_gen=cg)).reshape(cols, n)
+                    got = ib.ntt(field, x.reshape(-1, 1), n, d, ib.NTTConfig(batch_size=cols, columns_batch=True, ordering=o, coset_gen=cg))
+                    assert np.array_equal(got.reshape(n, cols), rows.T), (name, logn, cols, d, o, cg is not None)
+        os.environ["B200_NTT_COLUMNS_STRIDED"] = "1"
+        try:
+            old = ib.ntt(field, x.reshape(-1, 1), n, ib.NTTDir.kForward, ib.NTTConfig(batch_size=cols, columns_batch=True, coset_gen=g))
+        finally:
+            del os.environ["B200_NTT_COLUMNS_STRIDED"]
+        dx = ib.to_device(x.reshape(-1, 1))
+        ib.ntt(field, dx, n, ib.NTTDir.kForward, ib.NTTConfig(batch_size=cols, columns_batch=True, coset_gen=g, are_outputs_on_device=True), dx)
+        assert np.array_equal(ib.to_host(dx).reshape(-1, 1), old), (name, logn, cols)
+    ib.ntt_release_domain(field)

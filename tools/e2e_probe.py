@@ -9,7 +9,7 @@ import icicle_b200 as ib
 import bench
 
 logn = int(sys.argv[1]) if len(sys.argv) > 1 else 26
-chunk_list = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [4, 8, 16]
+chunk_list = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 4, 8]
 n = 1 << logn
 dev = torch.device("cuda", 0)
 ib.set_device(0)
@@ -27,7 +27,10 @@ del scalars, points
 torch.cuda.empty_cache()
 h_res = np.zeros((1, 24), dtype=np.uint32)
 for ch in chunk_list:
-    os.environ["B200_MSM_PIPELINE_CHUNKS"] = str(ch)
+    if ch > 0:
+        os.environ["B200_MSM_PIPELINE_CHUNKS"] = str(ch)      # k equal chunks
+    else:
+        os.environ.pop("B200_MSM_PIPELINE_CHUNKS", None)      # 0 = the default graded schedule
     ib.msm(C_, h_s, h_p, n, ib.MSMConfig(), h_res)
     ts = []
     for _ in range(3):
