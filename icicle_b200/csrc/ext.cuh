@@ -81,6 +81,44 @@ B200_D F load_el(const uint32_t* p)
 {
   return load_el(p, (F*)nullptr);
 }
+// Gather loads.  Random 32-byte reads are bound by the number of load REQUESTS as much as by sectors on B200: one 256-bit load
+// (sm_100+: LDG.E.ENL2.256) per 32-byte coordinate instead of two 128-bit ones raises the measured random-gather rate from
+// 30 to 48 G gathers/s (tools/gather_bench.cu, profiles/r1_gather_qualifiers.txt).  `wide` = the base pointer is 32-byte
+// aligned (our own staging copies always are; a caller's device buffer is checked on the host).  Read-only data (ld.global.nc).
+template <class P>
+B200_D Fp<P> load_fp_gather(const uint32_t* p, bool wide)
+{
+#ifdef __CUDA_ARCH__
+  if constexpr (P::N % 8 == 0) {
+    if (wide) {
+      Fp<P> r;
+#pragma unroll
+      for (int i = 0; i < P::N; i += 8)
+        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.v[i]), "=r"(r.v[i + 1]), "=r"(r.v[i + 2]), "=r"(r.v[i + 3]), "=r"(r.v[i + 4]), "=r"(r.v[i + 5]), "=r"(r.v[i + 6]), "=r"(r.v[i + 7])
+                     : "l"(p + i));
+      return r;
+    }
+  }
+#endif
+  return load_fp<Fp<P>>(p);
+}
+template <class P>
+B200_D Fp2<P> load_el_gather(const uint32_t* p, bool wide, Fp2<P>*)
+{
+  return {load_fp_gather<P>(p, wide), load_fp_gather<P>(p + P::N, wide)};
+}
+template <class P>
+B200_D Fp<P> load_el_gather(const uint32_t* p, bool wide, Fp<P>*)
+{
+  return load_fp_gather<P>(p, wide);
+}
+template <class F>
+B200_D F load_el_gather(const uint32_t* p, bool wide)
+{
+  return load_el_gather(p, wide, (F*)nullptr);
+}
+
 template <class P>
 B200_D void store_el(uint32_t* p, const Fp2<P>& a)
 {

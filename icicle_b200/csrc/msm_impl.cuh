@@ -44,9 +44,9 @@ struct alignas(16) AffineRaw {
 };
 
 template <class F>
-B200_D Affine<F> load_affine(const uint32_t* p)
+B200_D Affine<F> load_affine(const uint32_t* p, bool wide = false)
 {
-  return {load_el<F>(p), load_el<F>(p + F::N)};
+  return {load_el_gather<F>(p, wide), load_el_gather<F>(p + F::N, wide)};
 }
 template <class F>
 B200_D XYZZ<F> load_xyzz(const uint32_t* p)
@@ -134,7 +134,7 @@ template <class F, bool DIRECT>
 __global__ void __launch_bounds__(MSM_THREADS) k_accumulate(
   const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n_entries, const uint32_t* __restrict__ n_dev, uint32_t slice,
   uint32_t sentinel, const uint32_t* __restrict__ points, uint32_t* __restrict__ buckets, uint32_t* __restrict__ pkey,
-  uint32_t* __restrict__ pflag, uint32_t* __restrict__ ppt, uint64_t n_slices)
+  uint32_t* __restrict__ pflag, uint32_t* __restrict__ ppt, uint64_t n_slices, bool wide)
 {
   constexpr int AW = 2 * F::N, XW = 4 * F::N;
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(MSM_THREADS) k_accumulate(
   XYZZ<F> acc = XYZZ<F>::inf();
 
   uint32_t v = DIRECT ? (uint32_t)beg : vals[beg];
-  Affine<F> nxt = load_affine<F>(points + (uint64_t)(v & ~SIGN_BIT) * AW);
+  Affine<F> nxt = load_affine<F>(points + (uint64_t)(v & ~SIGN_BIT) * AW, wide);
   bool nxt_neg = !DIRECT && (v & SIGN_BIT) != 0;
 
   for (uint64_t e = beg; e < end; e++) {
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(MSM_THREADS) k_accumulate(
     if (e + 1 < n_entries) knext = keys[e + 1];
     if (e + 1 < end && knext != sentinel) {
       uint32_t v2 = DIRECT ? (uint32_t)(e + 1) : vals[e + 1];
-      nxt = load_affine<F>(points + (uint64_t)(v2 & ~SIGN_BIT) * AW);
+      nxt = load_affine<F>(points + (uint64_t)(v2 & ~SIGN_BIT) * AW, wide);
       nxt_neg = !DIRECT && (v2 & SIGN_BIT) != 0;
     }
     if (neg) p.y = p.y.neg();
@@ -574,6 +574,7 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
     const uint32_t sentinel = (uint32_t)n_buckets;
     const uint32_t* sc = (const uint32_t*)d_scal + (uint64_t)b0 * n * S::N;
     const uint32_t* pts = pts_m + (shared ? 0 : (uint64_t)b0 * n * pl.pf * AW);
+    const bool pts_wide = (((uintptr_t)pts) & 31u) == 0 && (F::BYTES % 32 == 0) && !getenv("B200_MSM_NO_WIDE_LOADS");
 
     if (do_acc) {
     // K6
@@ -598,7 +599,7 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
       n_slices = (n_ent + slice - 1) / slice;
       k_accumulate<F, false><<<(unsigned)((n_slices + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
         dk.Current(), dv.Current(), n_ent, nullptr, slice, sentinel, pts, bkt, s_pkey.as<uint32_t>(),
-        s_pflag.as<uint32_t>(), s_ppt.as<uint32_t>(), n_slices); B200_LAUNCHED(1);
+        s_pflag.as<uint32_t>(), s_ppt.as<uint32_t>(), n_slices, pts_wide); B200_LAUNCHED(1);
       B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     } else {
       const uint32_t nb = (uint32_t)n_buckets;
@@ -624,10 +625,10 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
         const uint64_t ocap = cap[(l & 1) + 1];
         const bool last = (l + 1 == levels);
         if (l == 0) {
-          PairSrc<F, true> src = {lk, dv.Current(), lp, 0};
+          PairSrc<F, true> src = {lk, dv.Current(), lp, 0, pts_wide};
           k_pair_prefix<F, true><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, nb, PAIR_J, pbuf, pcap, tree);
         } else {
-          PairSrc<F, false> src = {lk, nullptr, lp, lcap};
+          PairSrc<F, false> src = {lk, nullptr, lp, lcap, false};
           k_pair_prefix<F, false><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, nb, PAIR_J, pbuf, pcap, tree);
         }
         B200_LAUNCHED(1);
@@ -653,11 +654,11 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
           }
         }
         if (l == 0) {
-          PairSrc<F, true> src = {lk, dv.Current(), lp, 0};
+          PairSrc<F, true> src = {lk, dv.Current(), lp, 0, pts_wide};
           if (last) k_pair_apply<F, true, false><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, off_n, nb, PAIR_J, pbuf, pcap, tree, out_p, ocap, out_k);
           else k_pair_apply<F, true, true><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, off_n, nb, PAIR_J, pbuf, pcap, tree, out_p, ocap, out_k);
         } else {
-          PairSrc<F, false> src = {lk, nullptr, lp, lcap};
+          PairSrc<F, false> src = {lk, nullptr, lp, lcap, false};
           if (last) k_pair_apply<F, false, false><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, off_n, nb, PAIR_J, pbuf, pcap, tree, out_p, ocap, out_k);
           else k_pair_apply<F, false, true><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, off_n, nb, PAIR_J, pbuf, pcap, tree, out_p, ocap, out_k);
         }
@@ -670,7 +671,7 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
       n_slices = (capl + slice - 1) / slice;
       k_accumulate<F, true><<<(unsigned)((n_slices + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
         lk, nullptr, 0, s_off[levels & 1].as<uint32_t>() + nb, slice, 0xffffffffu, lp, bkt, s_pkey.as<uint32_t>(),
-        s_pflag.as<uint32_t>(), s_ppt.as<uint32_t>(), n_slices); B200_LAUNCHED(1);
+        s_pflag.as<uint32_t>(), s_ppt.as<uint32_t>(), n_slices, true); B200_LAUNCHED(1); // level buffers are our own (aligned) scratch
       B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     }
     prof.mark("accumulate");

@@ -180,6 +180,7 @@ struct PairSrc {
   const uint32_t* vals;
   const uint32_t* pts;
   uint64_t cap;
+  bool wide; // GATHER: pts is 32-byte aligned -> 256-bit gather loads (ext.cuh load_el_gather)
   B200_D void load_x(uint32_t e, F& x, uint32_t& ref) const
   {
     if constexpr (GATHER) {
@@ -189,6 +190,25 @@ struct PairSrc {
       ref = e;
       x = load_planar<F>(reinterpret_cast<const uint4*>(pts), cap, e);
     }
+  }
+  // --- split accessors for the software pipeline: the (key, value) words are prefetched two slots ahead, the coordinates one
+  // slot ahead, and nothing touches a loaded register before the slot is consumed (a sign flip inside the fetch would make
+  // the warp wait for the gather right there: ncu, profiles/r1_ncu_pair_kernels_2p26.txt)
+  B200_D uint32_t ref_of(uint32_t e, uint32_t v) const { return GATHER ? v : e; }
+  B200_D F load_x_raw(uint32_t ref) const
+  {
+    if constexpr (GATHER) return load_el_gather<F>(pts + (uint64_t)(ref & ~PAIR_SIGN_BIT) * AW, wide);
+    else return load_planar<F>(reinterpret_cast<const uint4*>(pts), cap, ref);
+  }
+  B200_D F load_y_raw(uint32_t ref) const
+  {
+    if constexpr (GATHER) return load_el_gather<F>(pts + (uint64_t)(ref & ~PAIR_SIGN_BIT) * AW + N, wide);
+    else return load_planar<F>(reinterpret_cast<const uint4*>(pts) + (uint64_t)(N / 4) * cap, cap, ref);
+  }
+  B200_D F signed_y(uint32_t ref, const F& y) const
+  {
+    if constexpr (GATHER) return (ref & PAIR_SIGN_BIT) ? y.neg() : y;
+    else return y;
   }
   B200_D F load_y(uint32_t ref) const // sign applied
   {
@@ -218,24 +238,43 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_prefix(
   const uint64_t tid = (uint64_t)blockIdx.x * PAIR_THREADS + threadIdx.x;
   uint64_t q = (uint64_t)blockIdx.x * J * PAIR_THREADS + threadIdx.x;
   F run = F::one();
-  // software pipeline: the x coordinates of slot j+1 are in flight while the product of slot j runs
+  // software pipeline, two deep: the (key, value) words of slot j+2 and the x coordinates of slot j+1 are in flight while the
+  // product of slot j runs (level 0 chases keys -> point index -> point: three dependent DRAM accesses per slot otherwise)
+  struct Idx {
+    uint2 kk, vv;
+    bool ok;
+  };
+  auto fetch_idx = [&](uint64_t qq, Idx& ix) {
+    ix.ok = (2 * qq + 1 < n);
+    ix.kk = make_uint2(0u, 1u);
+    ix.vv = make_uint2(0u, 0u);
+    if (ix.ok) {
+      ix.kk = *reinterpret_cast<const uint2*>(src.keys + 2 * qq);
+      if constexpr (GATHER) ix.vv = *reinterpret_cast<const uint2*>(src.vals + 2 * qq);
+    }
+  };
   bool have = false, nhave = false;
   F x1, x2, nx1, nx2;
   uint32_t r1 = 0, r2 = 0, nr1 = 0, nr2 = 0;
-  auto fetch = [&](uint64_t qq, bool& hv, F& a, F& b, uint32_t& ra, uint32_t& rb_) {
-    hv = false;
-    if (2 * qq + 1 < n) {
-      const uint2 kk = *reinterpret_cast<const uint2*>(src.keys + 2 * qq);
-      if (kk.x == kk.y) {
-        hv = true;
-        src.load_x((uint32_t)(2 * qq), a, ra);
-        src.load_x((uint32_t)(2 * qq + 1), b, rb_);
-      }
+  auto fetch_pts = [&](uint64_t qq, const Idx& ix, bool& hv, F& a, F& b, uint32_t& ra, uint32_t& rb_) {
+    hv = ix.ok && ix.kk.x == ix.kk.y;
+    if (hv) {
+      ra = src.ref_of((uint32_t)(2 * qq), ix.vv.x);
+      rb_ = src.ref_of((uint32_t)(2 * qq + 1), ix.vv.y);
+      a = src.load_x_raw(ra);
+      b = src.load_x_raw(rb_);
     }
   };
-  fetch(q, have, x1, x2, r1, r2);
+  Idx i0, i1, i2;
+  fetch_idx(q, i0);
+  i1.ok = false; i1.kk = make_uint2(0u, 1u); i1.vv = make_uint2(0u, 0u);
+  if (J > 1) fetch_idx(q + PAIR_THREADS, i1);
+  fetch_pts(q, i0, have, x1, x2, r1, r2);
   for (uint32_t j = 0; j < J; j++) {
-    if (j + 1 < J) fetch(q + PAIR_THREADS, nhave, nx1, nx2, nr1, nr2);
+    i2.ok = false; i2.kk = make_uint2(0u, 1u); i2.vv = make_uint2(0u, 0u);
+    if (j + 2 < J) fetch_idx(q + 2 * PAIR_THREADS, i2);
+    nhave = false;
+    if (j + 1 < J) fetch_pts(q + PAIR_THREADS, i1, nhave, nx1, nx2, nr1, nr2);
     if (have) {
       F d;
       if (x1 == x2 || x1.is_zero() || x2.is_zero()) { // rare: the y coordinates decide what kind of sum this is
@@ -249,7 +288,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_prefix(
       run = fmul(run, d);
     }
     have = nhave; x1 = nx1; x2 = nx2; r1 = nr1; r2 = nr2;
-    nhave = false;
+    i1 = i2;
     q += PAIR_THREADS;
   }
   store_el(totals + tid * N, run);
@@ -332,7 +371,7 @@ B200_D void pair_store_point(uint32_t* __restrict__ out_pts, uint64_t ocap, uint
 }
 
 template <class F, bool GATHER, bool OUT_PLANAR>
-__global__ void __launch_bounds__(PAIR_THREADS) k_pair_apply(
+__global__ void __launch_bounds__(PAIR_THREADS, (F::BYTES <= 32) ? 4 : 1) k_pair_apply(
   PairSrc<F, GATHER> src, const uint32_t* __restrict__ off, const uint32_t* __restrict__ off_next, uint32_t nb, uint32_t J,
   const uint4* __restrict__ pbuf, uint64_t pcap, const uint32_t* __restrict__ totals_inv, uint32_t* __restrict__ out_pts, uint64_t ocap,
   uint32_t* __restrict__ out_keys)
@@ -346,36 +385,66 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_apply(
 
   struct In {
     uint32_t k1, k2, r1, r2;
+    uint32_t o1, o2; // offset-table words the output position needs (real pair: off[k1], off_next[k1]; else off_next[k1 + 1], off_next[k2])
     int state; // 0 = nothing, 1 = one entry only, 2 = two entries of different buckets, 3 = real pair
-    F x1, y1, x2, y2, pre;
+    F x1, y1, x2, y2, pre; // y as stored: the sign of a gathered entry is applied when the slot is consumed
   };
-  auto fetch = [&](uint64_t qq, In& in) {
-    in.state = 0;
+  // two-deep software pipeline (see k_pair_prefix): index words two slots ahead, coordinates one slot ahead
+  struct Idx {
+    uint2 kk, vv;
+    int cnt; // entries of the slot that exist: 0, 1 or 2
+  };
+  auto fetch_idx = [&](uint64_t qq, Idx& ix) {
     const uint64_t e0 = 2 * qq;
-    if (e0 >= n) return;
-    if (e0 + 1 < n) {
-      const uint2 kk = *reinterpret_cast<const uint2*>(src.keys + e0);
-      in.k1 = kk.x; in.k2 = kk.y;
-      in.state = (kk.x == kk.y) ? 3 : 2;
-    } else {
-      in.k1 = src.keys[e0];
-      in.state = 1;
+    ix.cnt = (e0 + 1 < n) ? 2 : ((e0 < n) ? 1 : 0);
+    ix.kk = make_uint2(0u, 0u);
+    ix.vv = make_uint2(0u, 0u);
+    if (ix.cnt == 2) {
+      ix.kk = *reinterpret_cast<const uint2*>(src.keys + e0);
+      if constexpr (GATHER) ix.vv = *reinterpret_cast<const uint2*>(src.vals + e0);
+    } else if (ix.cnt == 1) {
+      ix.kk.x = src.keys[e0];
+      if constexpr (GATHER) ix.vv.x = src.vals[e0];
     }
-    src.load_x((uint32_t)e0, in.x1, in.r1);
-    in.y1 = src.load_y(in.r1);
+  };
+  auto fetch_pts = [&](uint64_t qq, const Idx& ix, In& in) {
+    in.state = (ix.cnt == 2) ? ((ix.kk.x == ix.kk.y) ? 3 : 2) : ix.cnt;
+    if (in.state == 0) return;
+    in.k1 = ix.kk.x; in.k2 = ix.kk.y;
+    in.r1 = src.ref_of((uint32_t)(2 * qq), ix.vv.x);
+    in.x1 = src.load_x_raw(in.r1);
+    in.y1 = src.load_y_raw(in.r1);
     if (in.state >= 2) {
-      src.load_x((uint32_t)e0 + 1, in.x2, in.r2);
-      in.y2 = src.load_y(in.r2);
+      in.r2 = src.ref_of((uint32_t)(2 * qq + 1), ix.vv.y);
+      in.x2 = src.load_x_raw(in.r2);
+      in.y2 = src.load_y_raw(in.r2);
     }
-    if (in.state == 3) in.pre = load_planar<F>(pbuf, pcap, qq);
+    if (in.state == 3) {
+      in.pre = load_planar<F>(pbuf, pcap, qq);
+      in.o1 = off[in.k1];
+      in.o2 = off_next[in.k1];
+    } else {
+      in.o1 = off_next[in.k1 + 1];
+      in.o2 = (in.state == 2) ? off_next[in.k2] : 0u;
+    }
   };
 
   In cur, nxt;
+  Idx i0, i1, i2;
   uint64_t q = q0 + (uint64_t)(J - 1) * PAIR_THREADS;
-  fetch(q, cur);
+  fetch_idx(q, i0);
+  i1.cnt = 0; i1.kk = make_uint2(0u, 0u); i1.vv = make_uint2(0u, 0u);
+  if (J > 1) fetch_idx(q - PAIR_THREADS, i1);
+  fetch_pts(q, i0, cur);
   for (uint32_t j = J; j-- > 0;) {
+    i2.cnt = 0; i2.kk = make_uint2(0u, 0u); i2.vv = make_uint2(0u, 0u);
+    if (j > 1) fetch_idx(q - 2 * PAIR_THREADS, i2);
     nxt.state = 0;
-    if (j > 0) fetch(q - PAIR_THREADS, nxt);
+    if (j > 0) fetch_pts(q - PAIR_THREADS, i1, nxt);
+    if (cur.state != 0) {
+      cur.y1 = src.signed_y(cur.r1, cur.y1);
+      if (cur.state >= 2) cur.y2 = src.signed_y(cur.r2, cur.y2);
+    }
     if (cur.state == 3) {
       int kind;
       const F d = pair_denominator(cur.x1, cur.y1, cur.x2, cur.y2, kind);
@@ -400,23 +469,24 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_pair_apply(
       } else {
         x3 = F::zero(); y3 = F::zero();
       }
-      const uint32_t rb = off[cur.k1];
+      const uint32_t rb = cur.o1;
       const uint32_t a = rb + (rb & 1u);
-      const uint32_t slot = off_next[cur.k1] + (rb & 1u) + (((uint32_t)(2 * q) - a) >> 1);
+      const uint32_t slot = cur.o2 + (rb & 1u) + (((uint32_t)(2 * q) - a) >> 1);
       pair_store_point<F, OUT_PLANAR>(out_pts, ocap, slot, x3, y3);
       out_keys[slot] = cur.k1;
     } else if (cur.state != 0) {
       // entry 2q is the last of its run; entry 2q+1 (if any) is the first of the next non-empty run
-      const uint32_t s1 = off_next[cur.k1 + 1] - 1;
+      const uint32_t s1 = cur.o1 - 1;
       pair_store_point<F, OUT_PLANAR>(out_pts, ocap, s1, cur.x1, cur.y1);
       out_keys[s1] = cur.k1;
       if (cur.state == 2) {
-        const uint32_t s2 = off_next[cur.k2];
+        const uint32_t s2 = cur.o2;
         pair_store_point<F, OUT_PLANAR>(out_pts, ocap, s2, cur.x2, cur.y2);
         out_keys[s2] = cur.k2;
       }
     }
     cur = nxt;
+    i1 = i2;
     q -= PAIR_THREADS;
   }
 }

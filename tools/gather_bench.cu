@@ -20,6 +20,14 @@ __device__ __forceinline__ uint4 ldg(const uint4* p)
   return r;
 }
 
+// 256-bit loads (sm_100+: LDG.E.ENL2.256): one request per 32-byte sector instead of two
+__device__ __forceinline__ uint32_t ldg256(const uint4* p)
+{
+  uint32_t r0, r1, r2, r3, r4, r5, r6, r7;
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "l"(p));
+  return r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7;
+}
+
 // each thread gathers `per` random records of BYTES bytes (16-byte pieces) from a table of n_rec 64-byte records
 template <int MODE, int BYTES>
 __global__ void k_gather(const uint4* __restrict__ table, uint32_t rec_mask, uint32_t per, uint32_t* out)
@@ -31,10 +39,15 @@ __global__ void k_gather(const uint4* __restrict__ table, uint32_t rec_mask, uin
     x = x * 1664525u + 1013904223u;
     const uint32_t rec = (x >> 4) & rec_mask;
     const uint4* p = table + (uint64_t)rec * 4; // 64-byte records
+    if (MODE == 7) {
 #pragma unroll
-    for (int k = 0; k < BYTES / 16; k++) {
-      uint4 v = ldg<MODE>(p + k);
-      acc += v.x ^ v.y ^ v.z ^ v.w;
+      for (int k = 0; k < BYTES / 32; k++) acc += ldg256(p + 2 * k);
+    } else {
+#pragma unroll
+      for (int k = 0; k < BYTES / 16; k++) {
+        uint4 v = ldg<MODE>(p + k);
+        acc += v.x ^ v.y ^ v.z ^ v.w;
+      }
     }
   }
   if (acc == 0x12345678u) out[t] = acc;
@@ -79,6 +92,7 @@ int main()
   RUN(4, "ld.global.nc.L1::no_allocate.L2::64B")
   RUN(5, "ld.global.cs")
   RUN(6, "ld.global.L1::evict_first.L2::64B")
+  RUN(7, "ld.global.nc.v8.u32 (256-bit)")
   cudaError_t e = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(e));
   return e != cudaSuccess;
