@@ -35,11 +35,12 @@ ALG_BYTES_PER_POINT = 96  # |scalar_t| + |affine_t| for BN254 G1
 ALG_BYTES_PER_NTT_ELEM = 64  # one read + one write of a 32-byte element
 IMAD_WIDE_PEAK = 9.26e12  # measured on this pool's B200 (tools/imad_bench.cu, profiles/r1_imad_microbench.txt): IMAD.WIDE.U32.X thread-instr/s
 IMAD_WIDE_PER_MADD = 10 * 140  # 8M+2S Montgomery products per mixed add x 140 IMAD(.WIDE) per 8-limb product (cuobjdump)
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_accumulate launch at the headline config (2^26 points, c = 20), from
-# `ncu --set full` (profiles/r1_ncu_full_k_accumulate_2p26_raw.csv): 122.69 GB + 1.96 GB.  It is ~19x the algorithmic 6.44 GB
-# because every point (64 B) is gathered once per window (13x) and the sorted (key, index) lists are read too; the kernel
-# is integer-multiply bound (sm throughput 87 %, DRAM 10.8 % of peak), so this traffic is not what limits it.
-NCU_TRAFFIC_BYTES = {(26, 20): 124.65e9}
+# dram__bytes_read.sum + dram__bytes_write.sum of the bucket-accumulation stage of ONE MSM at the headline config (2^26 points,
+# c = 20, 5 pair levels): all k_pair_prefix / k_pair_apply / k_inv_* launches + k_accumulate, from the ncu launch list
+# profiles/r1_ncu_launches_msm_2p26.txt (218.4 GB read + 89.4 GB write).  It is ~48x the algorithmic 6.44 GB: level 0 gathers
+# every point once per window in each of its two passes and every level writes its halved list (planar scratch); the stage is
+# bound by the random-sector rate of HBM at level 0 and by IMAD.WIDE issue above it, not by bytes.
+NCU_TRAFFIC_BYTES = {(26, 20): 307.8e9}
 
 
 def hbm_peak():
@@ -120,7 +121,7 @@ def synth_inputs(torch, ib, logn, seed, device):
     return s.contiguous(), pts
 
 
-def run_reference_arm(args, rank):
+def run_reference_arm(args, rank, out_fd):
     """--impl reference: the reference's own CPU MSM (all host threads) on a bounded sample of the workload."""
     if rank != 0:
         return
@@ -149,7 +150,7 @@ def run_reference_arm(args, rank):
                          "sample": f"icicle CPU backend (oracle/_ref, g++ -O3, Taskflow stand-in) MSM of 2^{sample_log} points, mean of {args.steps}"},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(out_fd, line)
 
 
 def cpu_baseline(budget_s=20.0):
@@ -178,6 +179,21 @@ def cpu_baseline(budget_s=20.0):
 
 
 def main():
+    # exactly ONE line on stdout (the JSON): library chatter (e.g. "NCCL version ..." under torchrun) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main(real_stdout)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+
+
+def emit(fd, line):
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
+def _main(out_fd):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -198,7 +214,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference_arm(args, rank)
+        run_reference_arm(args, rank, out_fd)
         return
 
     import torch
@@ -362,7 +378,7 @@ def main():
                        "l2": "inputs (6 GiB at 2^26) exceed the 126 MB L2, no flush needed", "multi_gpu": "point-sharded; one NCCL all-gather of 96 B partials + ec_sum kernel"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "secondary": ntt,
         }
-        print(json.dumps(line), flush=True)
+        emit(out_fd, line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -26,11 +26,12 @@ class Field(enum.IntEnum):
     STARK252 = 7
     BABYBEAR = 8
     KOALABEAR = 9
+    M31 = 10
 
 
 FIELD_NAMES = {Field.BN254_FR: "bn254_fr", Field.BN254_FQ: "bn254_fq", Field.BLS12_381_FR: "bls12_381_fr",
                Field.BLS12_381_FQ: "bls12_381_fq", Field.BLS12_377_FR: "bls12_377_fr", Field.BLS12_377_FQ: "bls12_377_fq",
-               Field.BW6_761_FQ: "bw6_761_fq", Field.STARK252: "stark252", Field.BABYBEAR: "babybear", Field.KOALABEAR: "koalabear"}
+               Field.BW6_761_FQ: "bw6_761_fq", Field.STARK252: "stark252", Field.BABYBEAR: "babybear", Field.KOALABEAR: "koalabear", Field.M31: "m31"}
 
 
 class Curve(enum.IntEnum):

@@ -165,6 +165,7 @@ static inline int num_sms()
     B200_FIELD_CASE(B200_FIELD_STARK252, stark252, __VA_ARGS__)                                                        \
     B200_FIELD_CASE(B200_FIELD_BABYBEAR, babybear, __VA_ARGS__)                                                        \
     B200_FIELD_CASE(B200_FIELD_KOALABEAR, koalabear, __VA_ARGS__)                                                      \
+    B200_FIELD_CASE(B200_FIELD_M31, m31, __VA_ARGS__)                                                                  \
   default:                                                                                                             \
     return B200_INVALID_ARGUMENT;                                                                                      \
   }
@@ -190,7 +191,7 @@ static inline int field_limbs(int field)
   case B200_FIELD_STARK252: return 8;
   case B200_FIELD_BLS12_381_FQ: case B200_FIELD_BLS12_377_FQ: return 12;
   case B200_FIELD_BW6_761_FQ: return 24;
-  case B200_FIELD_BABYBEAR: case B200_FIELD_KOALABEAR: return 1;
+  case B200_FIELD_BABYBEAR: case B200_FIELD_KOALABEAR: case B200_FIELD_M31: return 1;
   default: return 0;
   }
 }

@@ -594,6 +594,18 @@ int b200_convert_montgomery(int field, const void* in, uint64_t size, int is_int
 {
   if (!cfg || !in || !out) return B200_INVALID_POINTER;
   const uint64_t n = size * (cfg->batch_size > 0 ? cfg->batch_size : 1);
+  if (field == B200_FIELD_M31) { // the reference's MersenneField: to/from_montgomery are the identity (m31.h:232-234)
+    cudaStream_t s = (cudaStream_t)cfg->stream;
+    const size_t bytes = n * 4;
+    Scratch si, so;
+    const void* din;
+    void* dout;
+    int err;
+    if ((err = stage_in(din, in, bytes, cfg->is_a_on_device, s, si))) return err;
+    if ((err = stage_out(dout, out, bytes, cfg->is_result_on_device, s, so))) return err;
+    if (din != dout) B200_CUDA_TRY(cudaMemcpyAsync(dout, din, bytes, cudaMemcpyDeviceToDevice, s), B200_COPY_FAILED);
+    return finish_out(out, dout, bytes, cfg->is_result_on_device, cfg->is_async, s);
+  }
   B200_DISPATCH_FIELD(field, return convert_mont_impl<F>(in, n, is_into, cfg, out));
   return B200_INVALID_ARGUMENT;
 }

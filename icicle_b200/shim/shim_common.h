@@ -57,6 +57,8 @@ namespace b200_shim {
     return B200_FIELD_STARK252;
 #elif FIELD_ID == KOALA_BEAR
     return B200_FIELD_KOALABEAR;
+#elif FIELD_ID == M31
+    return B200_FIELD_M31;
 #else
     return -1;
 #endif

@@ -60,6 +60,7 @@ typedef enum {
   B200_FIELD_STARK252 = 7,     /* fields/stark_fields/stark252.h */
   B200_FIELD_BABYBEAR = 8,     /* fields/stark_fields/babybear.h */
   B200_FIELD_KOALABEAR = 9,    /* fields/stark_fields/koalabear.h */
+  B200_FIELD_M31 = 10,         /* fields/stark_fields/m31.h: vec-ops only (no NTT upstream); Montgomery form == standard form (m31.h:232-234) */
   B200_FIELD_COUNT
 } b200_field_t;
 

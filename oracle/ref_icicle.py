@@ -33,6 +33,7 @@ TARGETS = {
     "babybear": dict(curve=False, s=1),
     "koalabear": dict(curve=False, s=1),
     "stark252": dict(curve=False, s=8),
+    "m31": dict(curve=False, s=1),
 }
 
 

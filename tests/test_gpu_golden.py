@@ -145,3 +145,36 @@ def test_extension_ntt_golden(name, field):
     ib.ntt_extension(field, dx, n, 1, ib.NTTConfig(batch_size=2, are_outputs_on_device=True), dx)
     assert np.array_equal(ib.to_host(dx).reshape(-1, 4), x)
     ib.ntt_release_domain(field)
+
+
+def test_m31_vec_ops_golden():
+    """Mersenne-31 vec-ops (north_star's field list; vec-ops only upstream: icicle/cmake/features.cmake:7) vs the reference's
+    MersenneField outputs (tests/golden/m31.npz) incl. 0, 1, p-1 and the identity Montgomery conversion; inv / div / sum /
+    product against Python integers; the NTT entry point reports API_NOT_IMPLEMENTED like the reference build (no NTT feature)."""
+    g = gold("m31")
+    F = ib.Field.M31
+    p = utils.field_params("m31")["p"]
+    a, b = g["vec_a"], g["vec_b"]
+    n = a.shape[0]
+    assert np.array_equal(ib.vector_add(F, a, b, n), g["vector_add"])
+    assert np.array_equal(ib.vector_sub(F, a, b, n), g["vector_sub"])
+    assert np.array_equal(ib.vector_mul(F, a, b, n), g["vector_mul"])
+    acc = ib.to_device(a)
+    ib.vector_accumulate(F, acc, ib.to_device(b), n)
+    assert np.array_equal(ib.to_host(acc).reshape(-1, 1), g["vector_accumulate"])
+    assert np.array_equal(ib.convert_montgomery(F, a, n, True), g["to_montgomery"])
+    assert np.array_equal(ib.convert_montgomery(F, a, n, False), g["from_montgomery"])
+    assert np.array_equal(ib.bit_reverse(F, a, n), g["bit_reverse"])
+    ai = [int(v) for v in a[:, 0]]
+    nz = np.array([v if v else 5 for v in ai], dtype=np.uint32).reshape(-1, 1)
+    inv = ib.vector_inv(F, nz, n)
+    assert [int(v) for v in inv[:, 0]] == [pow(int(v), -1, p) for v in nz[:, 0]]
+    div = ib.vector_div(F, b, nz, n)
+    assert [int(v) for v in div[:, 0]] == [int(x) * pow(int(y), -1, p) % p for x, y in zip(b[:, 0], nz[:, 0])]
+    assert int(ib.vector_sum(F, a, n)[0, 0]) == sum(ai) % p
+    prod = 1
+    for v in nz[:, 0]:
+        prod = prod * int(v) % p
+    assert int(ib.vector_product(F, nz, n)[0, 0]) == prod
+    with pytest.raises(ib.IcicleError):
+        ib.ntt_init_domain(F, np.array([p - 1], dtype=np.uint32))

@@ -205,3 +205,18 @@ def test_port_extension_ntt_vs_reference_golden(name):
                 y = Y.reshape(-1, 4) if not col else np.ascontiguousarray(Y.transpose(1, 0, 2)).reshape(-1, 4)
                 key = f"l{logn}_b{batch}_c{col}_o{ordering}_d{d}_g{c}"
                 assert hashlib.sha256(np.ascontiguousarray(y).tobytes()).digest() == g["sha_" + key].tobytes(), key
+
+
+def test_m31_golden_vs_port_and_integers():
+    """tests/golden/m31.npz (tools/make_golden_m31.py, the reference's MersenneField): canonical results in [0, p), Montgomery
+    conversion = identity (m31.h:232-234); the C restatement's Barrett path and plain Python integers agree with it."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "m31.npz"))
+    p = utils.field_params("m31")["p"]
+    assert p == (1 << 31) - 1
+    a, b = [int(v) for v in g["vec_a"][:, 0]], [int(v) for v in g["vec_b"][:, 0]]
+    for op, f in (("vector_add", lambda x, y: (x + y) % p), ("vector_sub", lambda x, y: (x - y) % p), ("vector_mul", lambda x, y: x * y % p),
+                  ("vector_accumulate", lambda x, y: (x + y) % p)):
+        assert [int(v) for v in g[op][:, 0]] == [f(x, y) for x, y in zip(a, b)], op
+    for op in ("add", "sub", "mul"):
+        assert port.field_op("m31", op, a[:512], b[:512]) == [int(v) for v in g["vector_" + op][:512, 0]], op
+    assert np.array_equal(g["to_montgomery"], g["vec_a"]) and np.array_equal(g["from_montgomery"], g["vec_a"])

@@ -8,7 +8,7 @@ R^2, -p^-1 mod 2^32, 2-adicity, b in Montgomery form ...) is computed with Pytho
 
 Reference sources parsed (file under /root/reference/icicle/include/icicle):
   fields/snark_fields/{bn254,bls12_381,bls12_377,bw6_761}_{scalar,base}.h  (modulus, rou)
-  fields/stark_fields/{babybear,koalabear,stark252}.h                      (modulus, rou)
+  fields/stark_fields/{babybear,koalabear,stark252,m31}.h                      (modulus, rou)
   curves/params/{bn254,bls12_381,bls12_377,bw6_761,grumpkin}.h             (gen_x, gen_y, weierstrass_b, is_b_neg, G2)
 """
 import json, os, re, sys
@@ -58,6 +58,10 @@ FIELDS = [
     field("stark252", "fields/stark_fields/stark252.h", "stark252::fp_config"),
     field("babybear", "fields/stark_fields/babybear.h", "babybear::fp_config"),
     field("koalabear", "fields/stark_fields/koalabear.h", "koalabear::fp_config"),
+    # Mersenne-31: vec-ops only (no NTT in the reference: icicle/cmake/features.cmake:7).  The reference's MersenneField keeps
+    # values canonical and defines Montgomery form as the identity (m31.h:232-234); the kernels use the generic odd-modulus
+    # Montgomery arithmetic internally and b200_convert_montgomery copies (vec_ops.cu).
+    field("m31", "fields/stark_fields/m31.h", "m31::fp_config"),
 ]
 FBY = {f["name"]: f for f in FIELDS}
 
