@@ -46,6 +46,7 @@ int main()
     else if (f == "stark252") run<Fp<params::stark252>>(a, b);
     else if (f == "babybear") run<Fp<params::babybear>>(a, b);
     else if (f == "koalabear") run<Fp<params::koalabear>>(a, b);
+    else if (f == "m31") run<Fp<params::m31>>(a, b);
     else { printf("unknown\n"); }
   }
   return 0;
