@@ -487,7 +487,9 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
   const uint64_t max_slices = (max_ent + slice - 1) / slice;
 
   // chunk length for the bucket reduction: >= 64K threads if possible
-  int chunk_log = std::max(0, std::min(7, (pl.c - 1 + ilog2_ceil(max_modules)) - 16));
+  int chunk_target = 16; // log2 of the thread count k_bucket_chunks aims for
+  if (const char* ev = getenv("B200_MSM_CHUNK_TARGET")) chunk_target = std::max(10, std::min(22, atoi(ev)));
+  int chunk_log = std::max(0, std::min(7, (pl.c - 1 + ilog2_ceil(max_modules)) - chunk_target));
   if (chunk_log > pl.c - 1) chunk_log = pl.c - 1;
   const uint64_t max_chunks = max_buckets >> chunk_log;
 
