@@ -41,6 +41,9 @@ IMAD_WIDE_PER_MADD = 10 * 140  # 8M+2S Montgomery products per mixed add x 140 I
 # every point once per window in each of its two passes and every level writes its halved list (planar scratch); the stage is
 # bound by the random-sector rate of HBM at level 0 and by IMAD.WIDE issue above it, not by bytes.
 NCU_TRAFFIC_BYTES = {(26, 20): 307.8e9}
+# dram bytes of ONE forward BN254 NTT of 2^24 (3 k_ntt_tile passes; the first also reads the 0.5 GB twiddle table), from
+# profiles/r1_ncu_ntt_passes.txt; algorithmic = 1.07 GB
+NCU_NTT_TRAFFIC_BYTES = {24: 3.60e9}
 
 
 def hbm_peak():
@@ -361,7 +364,8 @@ def _main(out_fd):
             out[nm] = {"elements_per_s": (1 << nl) / (ms * 1e-3), "ms": ms}
         a = ALG_BYTES_PER_NTT_ELEM * (1 << nl) / (out["forward"]["ms"] * 1e-3) / 1e9
         ntt = {"metric": "bn254_ntt_elements_per_s", "logn": nl, "ordering": "kNN", **out,
-               "roofline": {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": None}}
+               "roofline": {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": NCU_NTT_TRAFFIC_BYTES.get(nl),
+                            "kernel": "k_ntt_tile<Fp<bn254_fr>> x 3 passes (IMAD.WIDE bound: sm 62-69 %, dram 9-12 %, profiles/r1_ncu_ntt_passes.txt)"}}
         ib.ntt_release_domain(F)
 
     cpu = None
