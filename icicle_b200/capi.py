@@ -79,6 +79,7 @@ SYMBOLS = {
     "b200_ec_sum": (_i, [_i, _vp, _i, C.POINTER(VecOpsConfigC), _vp]),
     "b200_msm_choose_c": (_i, [_i, _i, C.POINTER(MsmConfigC)]),
     "b200_msm_pair_levels": (_i, [_i, _i, C.POINTER(MsmConfigC)]),
+    "b200_msm_pipeline_schedule": (_i, [_i, C.POINTER(C.c_uint32), _i]),
     "b200_ntt_default_config": (None, [C.POINTER(NttConfigC)]),
     "b200_ntt_init_domain": (_i, [_i, _vp, _vp]),
     "b200_ntt_release_domain": (_i, [_i]),

@@ -59,6 +59,14 @@ __attribute__((visibility("hidden"))) int B200_CAT(b200_ecntt_entry_, B200_MSM_C
 {
   return EcnttEntry<ThisCurve>::run(input, size, dir, cfg, output, tw, aux, dom_log);
 }
+#if B200_MSM_CURVE == 0
+// planning query (host only, curve independent): the chunk sizes the host-pointer pipeline would use for an msm of `msm_size` points
+__attribute__((visibility("default"))) int b200_msm_pipeline_schedule(int msm_size, uint32_t* sizes, int max_chunks)
+{
+  if (msm_size <= 0 || !sizes || max_chunks <= 0) return -1;
+  return (int)pipeline_schedule((uint32_t)msm_size, sizes, (uint32_t)std::min(max_chunks, 32));
+}
+#endif
 __attribute__((visibility("hidden"))) int B200_CAT(b200_msm_plan_c_entry_, B200_MSM_CURVE)(int msm_size, const b200_msm_config* cfg)
 {
   return make_plan<ThisCurve>(msm_size, cfg).c;

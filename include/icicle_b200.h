@@ -141,6 +141,9 @@ B200_API int b200_msm_choose_c(int curve, int msm_size, const b200_msm_config* c
 /* number of batched-affine pair levels the MSM schedule runs before the XYZZ bucket accumulation (0 = XYZZ only); our own
  * planning query, no reference counterpart (the reference has no such stage: cpu_msm.hpp:259-314 adds point by point) */
 B200_API int b200_msm_pair_levels(int curve, int msm_size, const b200_msm_config* cfg);
+/* chunk sizes (points) of the host-pointer copy/compute pipeline for an msm of msm_size points (host scalars and points,
+ * batch 1, >= 2^23 points): returns the number of chunks written to sizes[0 .. max_chunks); our own planning query */
+B200_API int b200_msm_pipeline_schedule(int msm_size, uint32_t* sizes, int max_chunks);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * NTT -- replaces NttImpl / NttInitDomainImpl / NttReleaseDomainImpl / NttGetRouFromDomainImpl

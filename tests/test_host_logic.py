@@ -107,3 +107,36 @@ def test_point_sharded_msm_two_ranks_gloo(tmp_path):
              for r in range(2)]
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_pipeline_schedule(monkeypatch):
+    """Chunk schedule of the host-pointer MSM pipeline (msm_impl.cuh pipeline_schedule; pure host logic): covers every point
+    exactly once, starts with a small chunk (exposed H2D time) and ends with quarters (long bucket runs), honours the
+    equal-chunks override and the test override that allows tiny chunks."""
+    import ctypes as C
+    from icicle_b200 import capi
+    def sched(n):
+        buf = (C.c_uint32 * 32)()
+        k = capi.lib.b200_msm_pipeline_schedule(n, buf, 32)
+        return [buf[i] for i in range(k)]
+    monkeypatch.delenv("B200_MSM_PIPELINE_CHUNKS", raising=False)
+    monkeypatch.delenv("B200_MSM_PIPELINE_MIN", raising=False)
+    assert sched(1 << 26) == [1 << 22, 1 << 22, 1 << 23, 1 << 24, 1 << 24, 1 << 24]
+    for n in ((1 << 23), (1 << 23) + 12345, (1 << 25) - 1, (1 << 27) + 7, (1 << 30)):
+        s = sched(n)
+        assert sum(s) == n and 1 <= len(s) <= 6 and all(c >= 1 << 20 for c in s), (n, s)
+        assert s[0] <= max(n >> 4, 1 << 20)
+    assert sched(1 << 20) == [1 << 20]
+    monkeypatch.setenv("B200_MSM_PIPELINE_CHUNKS", "4")
+    assert sched(1 << 26) == [1 << 24] * 4
+    s = sched((1 << 24) + 3)
+    assert sum(s) == (1 << 24) + 3 and len(s) == 4
+    monkeypatch.setenv("B200_MSM_PIPELINE_MIN", "2")
+    monkeypatch.setenv("B200_MSM_PIPELINE_CHUNKS", "7")
+    s = sched(4113)
+    assert sum(s) == 4113 and len(s) == 7
+    monkeypatch.delenv("B200_MSM_PIPELINE_CHUNKS")
+    for n in (1, 2, 5, 100, 8203):
+        s = sched(n)
+        assert sum(s) == n and all(c > 0 for c in s), (n, s)
+    assert capi.lib.b200_msm_pipeline_schedule(0, (C.c_uint32 * 4)(), 4) == -1
