@@ -14,6 +14,8 @@
 // GPU schedule (one pass over the scalars, one gather pass over the points):
 //   K6  k_digits        scalar -> signed c-bit digits; emits (bucket key, point index|sign) per (scalar, window)
 //   K7  radix sort      (cub::DeviceRadixSort, library) groups entries by bucket
+//   K7' pair levels     (msm_pairs.cuh, large inputs) the sorted list is halved up to five times by batched-affine adds
+//                       (6 products per add, inversions shared across the grid) before the bucket accumulation
 //   K8  k_accumulate    each thread owns a fixed SLICE of the sorted entry list and sums runs of equal keys with
 //                       mixed XYZZ adds (8M+2S, Montgomery chains in registers); complete runs go straight to the
 //                       bucket, runs cut by a slice boundary become partials -> perfectly balanced for any scalar
@@ -22,8 +24,11 @@
 //   K9  k_bucket_chunks per-chunk running sums: sum_k (k+1)*B_k = triangle + offset*line
 //       k_sum_groups    tree-sum of chunk results per bucket module
 //   K10 k_final         Horner over bucket modules (c doublings each), XYZZ -> projective, out of Montgomery form
-// The bucket accumulation is integer-multiply bound (about 10 Montgomery products = 1400 IMAD.WIDE per point-window);
-// algorithmic HBM bytes are only |scalar| + |affine| per point (96 B for BN254 G1).
+// Host-pointer calls of >= 2^23 points run the same stages chunk by chunk behind the H2D copies (msm_pipelined): every chunk
+// accumulates into one shared bucket array (window size of the whole MSM), the reduction runs once.
+// The bucket accumulation is integer-multiply bound (6-10 Montgomery products of 140 IMAD.WIDE per point-window) except
+// level 0 of the pair tree, which is bound by HBM's random-sector rate; algorithmic HBM bytes are only |scalar| + |affine|
+// per point (96 B for BN254 G1).
 #pragma once
 #include "common.cuh"
 #include "msm_pairs.cuh"
@@ -722,9 +727,6 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
   }
   return B200_SUCCESS;
 }
-
-template <class F>
-__global__ void k_proj_sum(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out);
 
 // dst[k] += src[k] over two XYZZ bucket arrays (host-pointer pipeline: per-chunk bucket sums into the running ones)
 template <class F>
