@@ -220,3 +220,47 @@ def test_m31_golden_vs_port_and_integers():
     for op in ("add", "sub", "mul"):
         assert port.field_op("m31", op, a[:512], b[:512]) == [int(v) for v in g["vector_" + op][:512, 0]], op
     assert np.array_equal(g["to_montgomery"], g["vec_a"]) and np.array_equal(g["from_montgomery"], g["vec_a"])
+
+
+def test_ecntt_golden_vs_definition():
+    """tests/golden/bn254_ecntt.npz (tools/make_golden_ecntt.py, `bn254_ecntt` of the unmodified reference) against the defining
+    sums with Python-integer group arithmetic: forward out[k] = sum_i w^(ik) (g^i P_i), inverse out[i] = g^-i N^-1 sum_k w^(-ik) P_k,
+    kNR = bit-reversed output, kRN = bit-reversed input, columns batch = strided transforms (ntt_cpu.h:69-232 with E = projective_t)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bn254_ecntt.npz"))
+    q = utils.field_params("bn254_fq")["p"]
+    r = utils.field_params("bn254_fr")["p"]
+    n, batch, logn = 16, 2, 4
+    root = utils.from_limbs(g["ntt_root"].reshape(1, 8))[0]
+    w = pow(root, 1 << (int(g["dom_log"][0]) - logn), r)
+    coset = utils.from_limbs(g["coset"].reshape(1, 8))[0]
+    pts = [common.projective_to_affine_ints(p_, 8, q) for p_ in g["input_projective"]]
+    assert pts[3] is None                                             # the point at infinity in the input
+    rev = [common.bitrev(i, logn) for i in range(n)]
+
+    def transform(x, inverse, cg):
+        if not inverse:
+            xs = [common.ec_mul(pow(cg, i, r), x[i], q) if x[i] is not None else None for i in range(n)]
+            return [common.msm_naive_ints([pow(w, i * k, r) for i in range(n)], xs, q) for k in range(n)]
+        wi, ni, gi = pow(w, -1, r), pow(n, -1, r), pow(cg, -1, r)
+        out = []
+        for i in range(n):
+            acc = common.msm_naive_ints([pow(wi, i * k, r) for k in range(n)], x, q)
+            out.append(common.ec_mul(ni * pow(gi, i, r) % r, acc, q) if acc is not None else None)
+        return out
+
+    for d in (0, 1):
+        for o in (0, 1, 2):
+            for c in (0, 1):
+                exp = common.affine_limbs_to_ints(g[f"d{d}_o{o}_g{c}_affine"], 8)
+                for b in range(batch):
+                    x = pts[b * n:(b + 1) * n]
+                    if o == 2:
+                        x = [x[rev[i]] for i in range(n)]            # kRN: logical element i sits at position rev(i)
+                    y = transform(x, bool(d), coset if c else 1)
+                    if o == 1:
+                        y = [y[rev[i]] for i in range(n)]            # kNR: position i holds frequency rev(i)
+                    assert y == exp[b * n:(b + 1) * n], (d, o, c, b)
+    exp = common.affine_limbs_to_ints(g["d0_cols_affine"], 8)
+    for b in range(batch):
+        y = transform([pts[i * batch + b] for i in range(n)], False, 1)
+        assert y == [exp[i * batch + b] for i in range(n)], b
