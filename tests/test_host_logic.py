@@ -140,3 +140,21 @@ def test_pipeline_schedule(monkeypatch):
         s = sched(n)
         assert sum(s) == n and all(c > 0 for c in s), (n, s)
     assert capi.lib.b200_msm_pipeline_schedule(0, (C.c_uint32 * 4)(), 4) == -1
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's own CPU MSM on a bounded sample): exactly one JSON line on stdout with the
+    contract's keys; needs no GPU."""
+    import json
+    ref_icicle = pytest.importorskip("ref_icicle")
+    if not ref_icicle.available("bn254"):
+        pytest.skip("oracle/_ref/bn254 not built")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-sample-logn", "10"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, check=True).stdout
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "points/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0
