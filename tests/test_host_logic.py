@@ -158,3 +158,16 @@ def test_bench_reference_arm_contract():
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "points/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "reference" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_ec_host_emulation_matches_python_ints(tmp_path):
+    """Compiles icicle_b200/csrc/ec.cuh for the host and checks the XYZZ group law the MSM / ECNTT kernels run (mixed add, full
+    add on general representatives, doubling, chained adds, P + (-P), affine zero / infinity on either side) against
+    Python-integer curve arithmetic on BN254, BLS12-381 and Grumpkin -- the exact device code, carry flag emulated."""
+    exe = str(tmp_path / "ec_emul")
+    src = os.path.join(ROOT, "tests", "emul", "ec_emul_test.cpp")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-x", "c++", src, "-o", exe], check=True)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emul"))
+    import check_ec
+    n, m, bad = check_ec.run(exe, n_random=40, seed=7)
+    assert n == m and not bad, bad[:2]
