@@ -10,8 +10,8 @@
 #include <iostream>
 #define __host__
 #define __device__
-#include "../../icicle_b200/csrc/ec.cuh"
 #include "../../icicle_b200/csrc/ext.cuh"
+#include "../../icicle_b200/csrc/ec.cuh"
 using namespace b200;
 
 template <class F> static F parse(const std::string& h)
@@ -25,21 +25,30 @@ template <class F> static F parse(const std::string& h)
   }
   return r;
 }
-template <class F> static void print_el(const F& a)
+template <class P> static void print_el(const Fp<P>& a)
 {
-  F s = a.from_mont();
-  for (int i = F::N - 1; i >= 0; i--) printf("%08x", s.v[i]);
+  Fp<P> s = a.from_mont();
+  for (int i = P::N - 1; i >= 0; i--) printf("%08x", s.v[i]);
   printf(" ");
 }
+template <class P> static void print_el(const Fp2<P>& a) // "re im" as two words
+{
+  print_el(a.c0);
+  print_el(a.c1);
+}
+template <class P> static Fp2<P> parse2(const std::string& re, const std::string& im) { return {parse<Fp<P>>(re), parse<Fp<P>>(im)}; }
 template <class F> static void print_pt(const XYZZ<F>& q)
 {
   Projective<F> p = q.to_projective();
   print_el(p.x); print_el(p.y); print_el(p.z);
 }
+template <class F> static void run_pts(Affine<F> p1, Affine<F> p2, F z);
 template <class F> static void run(const std::string& x1, const std::string& y1, const std::string& x2, const std::string& y2, const std::string& zs)
 {
-  Affine<F> p1 = {parse<F>(x1).to_mont(), parse<F>(y1).to_mont()}, p2 = {parse<F>(x2).to_mont(), parse<F>(y2).to_mont()};
-  F z = parse<F>(zs).to_mont();
+  run_pts<F>({parse<F>(x1).to_mont(), parse<F>(y1).to_mont()}, {parse<F>(x2).to_mont(), parse<F>(y2).to_mont()}, parse<F>(zs).to_mont());
+}
+template <class F> static void run_pts(Affine<F> p1, Affine<F> p2, F z)
+{
   // mixed add
   XYZZ<F> a = XYZZ<F>::from_affine(p1);
   a.add_affine(p2);
@@ -65,7 +74,22 @@ template <class F> static void run(const std::string& x1, const std::string& y1,
 int main()
 {
   std::string c, x1, y1, x2, y2, z;
-  while (std::cin >> c >> x1 >> y1 >> x2 >> y2 >> z) {
+  while (std::cin >> c) {
+    if (c == "bn254_g2" || c == "bls12_381_g2") { // G2 over Fq2: every coordinate is "re im"
+      std::string w[10];
+      for (auto& t : w) std::cin >> t;
+      if (c == "bn254_g2") {
+        typedef params::bn254_fq P;
+        run_pts<Fp2<P>>({parse2<P>(w[0], w[1]).to_mont(), parse2<P>(w[2], w[3]).to_mont()}, {parse2<P>(w[4], w[5]).to_mont(), parse2<P>(w[6], w[7]).to_mont()},
+                        parse2<P>(w[8], w[9]).to_mont());
+      } else {
+        typedef params::bls12_381_fq P;
+        run_pts<Fp2<P>>({parse2<P>(w[0], w[1]).to_mont(), parse2<P>(w[2], w[3]).to_mont()}, {parse2<P>(w[4], w[5]).to_mont(), parse2<P>(w[6], w[7]).to_mont()},
+                        parse2<P>(w[8], w[9]).to_mont());
+      }
+      continue;
+    }
+    std::cin >> x1 >> y1 >> x2 >> y2 >> z;
     if (c == "bn254") run<Fp<params::bn254_fq>>(x1, y1, x2, y2, z);
     else if (c == "bls12_381") run<Fp<params::bls12_381_fq>>(x1, y1, x2, y2, z);
     else if (c == "grumpkin") run<Fp<params::bn254_fr>>(x1, y1, x2, y2, z);

@@ -163,7 +163,7 @@ def test_bench_reference_arm_contract():
 def test_ec_host_emulation_matches_python_ints(tmp_path):
     """Compiles icicle_b200/csrc/ec.cuh for the host and checks the XYZZ group law the MSM / ECNTT kernels run (mixed add, full
     add on general representatives, doubling, chained adds, P + (-P), affine zero / infinity on either side) against
-    Python-integer curve arithmetic on BN254, BLS12-381 and Grumpkin -- the exact device code, carry flag emulated."""
+    Python-integer curve arithmetic on BN254, BLS12-381, Grumpkin and the two G2 groups over Fq2 (ext.cuh) -- the exact device code, carry flag emulated."""
     exe = str(tmp_path / "ec_emul")
     src = os.path.join(ROOT, "tests", "emul", "ec_emul_test.cpp")
     subprocess.run(["g++", "-std=c++17", "-O1", "-x", "c++", src, "-o", exe], check=True)
