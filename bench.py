@@ -1,15 +1,22 @@
 #!/usr/bin/env python3
 """bench.py -- BN254 G1 MSM points/s @ 2^26 (headline) and BN254 NTT elements/s @ 2^24 (secondary), per BASELINE.json.
 
-    python bench.py --gpus N --steps K --warmup W [--impl b200|reference] [--logn 26] [--ntt-logn 24]
+    python bench.py --gpus N --steps K --warmup W [--impl b200|reference] [--logn 26] [--ntt-logn 24] [--no-configs]
 
 A step = one pass of the hot path over one batch of synthetic input: one MSM over 2^logn (scalar, point) pairs per GPU.
-  value       whole-job points/s with inputs resident in HBM (device-timed, CUDA events on the launching stream, max over ranks)
-  e2e         the same metric through the reference-facing C ABI with HOST (pinned) buffers: H2D of scalars+points and
-              D2H of the result inside the timed region
-  roofline    dominant kernel (k_accumulate): algorithmic bytes (96 B/point) / its CUDA-event duration vs the
-              measured HBM peak (MEASURED_PEAKS.json); the kernel is integer-multiply bound, see imad_frac
-  cpu_baseline the UNMODIFIED reference CPU backend (oracle/_ref, built from /root/reference sources) on a bounded sample
+  value        whole-job points/s with inputs resident in HBM (device-timed, CUDA events on the launching stream, max over ranks)
+  e2e          the same metric through the reference-facing PLUGIN call with HOST buffers, H2D of scalars+points and D2H of
+               the result inside the timed region.  e2e.value is what an unmodified ICICLE caller sees: the reference
+               frontend's own `bn254_msm` (oracle/_ref, Device{"CUDA"}) -> dispatcher -> registration shim -> C ABI, with
+               PAGEABLE host vectors (numpy arrays; what Rust/Go/C++ callers pass).  e2e.variants also lists the C-ABI call
+               with pageable and with pinned buffers.
+  roofline     dominant stage (bucket accumulation): algorithmic bytes (96 B/point) / its CUDA-event duration vs the
+               measured HBM peak (MEASURED_PEAKS.json); the stage is integer-multiply bound, see imad_frac
+  cpu_baseline the UNMODIFIED reference CPU backend (oracle/_ref: built from /root/reference sources with g++ -O3 and a Taskflow
+               STAND-IN thread pool -- upstream prefers clang + real Taskflow) on a bounded sample; the SAME bytes go through the
+               GPU and the results are compared -> parity_checked
+  configs      BASELINE configs 4 and 5 (BLS12-381 G1+G2 MSM 2^24 batch 8 with shared bases; BabyBear NTT 2^27 batch 128) sharded
+               by batch index over the N GPUs, and (N > 1) strong scaling of one 2^26 MSM split by point range
 N > 1 (torchrun): every rank runs the MSM over its own 2^logn-point shard of one (N * 2^logn)-point MSM; the partial results
 are combined with ONE NCCL all-gather (96 B per rank) + the ec_sum kernel -> "scaling": "weak".
 `--impl reference` times the reference's own CPU implementation (all host threads) on a bounded sample of the same
@@ -34,16 +41,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 ALG_BYTES_PER_POINT = 96  # |scalar_t| + |affine_t| for BN254 G1
 ALG_BYTES_PER_NTT_ELEM = 64  # one read + one write of a 32-byte element
 IMAD_WIDE_PEAK = 9.26e12  # measured on this pool's B200 (tools/imad_bench.cu, profiles/r1_imad_microbench.txt): IMAD.WIDE.U32.X thread-instr/s
-IMAD_WIDE_PER_MADD = 10 * 140  # 8M+2S Montgomery products per mixed add x 140 IMAD(.WIDE) per 8-limb product (cuobjdump)
 # dram__bytes_read.sum + dram__bytes_write.sum of the bucket-accumulation stage of ONE MSM at the headline config (2^26 points,
 # c = 20, 5 pair levels): all k_pair_prefix / k_pair_apply / k_inv_* launches + k_accumulate, from the ncu launch list
 # profiles/r1_ncu_launches_msm_2p26.txt (218.4 GB read + 89.4 GB write).  It is ~48x the algorithmic 6.44 GB: level 0 gathers
 # every point once per window in each of its two passes and every level writes its halved list (planar scratch); the stage is
 # bound by the random-sector rate of HBM at level 0 and by IMAD.WIDE issue above it, not by bytes.
 NCU_TRAFFIC_BYTES = {(26, 20): 307.8e9}
-# dram bytes of ONE forward BN254 NTT of 2^24 (3 k_ntt_tile passes; the first also reads the 0.5 GB twiddle table), from
-# profiles/r1_ncu_ntt_passes.txt; algorithmic = 1.07 GB
+# dram bytes of ONE forward BN254 NTT of 2^24 (3 k_ntt_tile passes), from profiles/; algorithmic = 1.07 GB
 NCU_NTT_TRAFFIC_BYTES = {24: 3.60e9}
+CPU_NOTE = "icicle CPU backend (oracle/_ref built from /root/reference sources with g++ -O3; Taskflow STAND-IN thread pool, not upstream's clang + Taskflow 3.8; auto window size)"
 
 
 def hbm_peak():
@@ -108,20 +114,51 @@ def pinned_array(ib, shape):
     return np.frombuffer(buf, dtype=np.uint32).reshape(shape), ptr
 
 
+def rand_scalars_dev(torch, n, seed, device, top=0x30644E72, limbs=8):
+    """n uniform scalars as (n, limbs) int32 on the device; top limb below the modulus' top limb -> always < p."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    s = torch.randint(-2 ** 31, 2 ** 31, (n, limbs), dtype=torch.int64, device=device, generator=g).to(torch.int32)
+    s[:, limbs - 1] = torch.randint(0, top, (n,), dtype=torch.int64, device=device, generator=g).to(torch.int32)
+    return s.contiguous()
+
+
 def synth_inputs(torch, ib, logn, seed, device):
-    """2^logn uniform scalars (top limb below the modulus' top limb -> always < p) and 2^logn points = 2^16 DISTINCT curve
-    points tiled (upstream's generator repeats only 100 points)."""
+    """2^logn uniform scalars and 2^logn points = 2^16 DISTINCT curve points tiled (upstream's generator
+    repeats only 100 points)."""
     import common
     n = 1 << logn
     distinct = min(n, 1 << 16)
     base = common.gen_g1_points("bn254", distinct, 1000 + seed)
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    s = torch.randint(-2 ** 31, 2 ** 31, (n, 8), dtype=torch.int64, device=device, generator=g).to(torch.int32)
-    top = torch.randint(0, 0x30644E72, (n,), dtype=torch.int64, device=device, generator=g).to(torch.int32)
-    s[:, 7] = top
-    pts = ib.to_device(base).repeat(n // distinct, 1).contiguous()
-    return s.contiguous(), pts
+    pts = ib.to_device(base, device).repeat(n // distinct, 1).contiguous()
+    return rand_scalars_dev(torch, n, seed, device), pts
+
+
+def load_reference(name="bn254"):
+    try:
+        import ref_icicle
+        if not ref_icicle.available(name):
+            return None
+        return ref_icicle.get(name)
+    except Exception:
+        return None
+
+
+def load_frontend_cuda(ref, local_rank):
+    """Make the reference frontend dispatch to our backend DSOs (build/backend/bn254) -- the drop-in path of tests/test_gpu_dropin.py."""
+    bdir = os.path.join(ROOT, "build", "backend", "bn254")
+    if ref is None or not os.path.exists(os.path.join(bdir, "libicicle_backend_cuda_device.so")):
+        return False
+    try:
+        if "CUDA" not in ref.registered_devices():
+            ref.load_backend(bdir)
+        if "CUDA" not in ref.registered_devices():
+            return False
+        ref.set_device("CUDA", local_rank)
+        ref.set_device("CPU", 0)
+        return True
+    except Exception:
+        return False
 
 
 def run_reference_arm(args, rank, out_fd):
@@ -150,35 +187,36 @@ def run_reference_arm(args, rank, out_fd):
         "data": "synthetic (reference generators: uniform scalars, 100 distinct points repeated)",
         "config": {"workload": f"BN254 G1 MSM 2^{args.logn} (bounded sample: 2^{sample_log} points per step on the host cores)"},
         "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "reference",
-                         "sample": f"icicle CPU backend (oracle/_ref, g++ -O3, Taskflow stand-in) MSM of 2^{sample_log} points, mean of {args.steps}"},
+                         "sample": f"{CPU_NOTE}; MSM of 2^{sample_log} points, mean of {args.steps}; per-step times {[round(x, 3) for x in ts]} s"},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(out_fd, line)
 
 
-def cpu_baseline(budget_s=20.0):
-    """Reference CPU backend on a bounded sample sized to ~10-20 s of CPU work."""
-    try:
-        import ref_icicle
-        r = ref_icicle.get("bn254")
-    except Exception as e:  # noqa
-        return {"value": None, "unit": "points/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
-    logn = 16
-    n = 1 << logn
-    s, P = r.generate_scalars(n), r.generate_affine_points(n)
-    r.msm(s, P, n)
-    t0 = time.perf_counter(); r.msm(s, P, n); t16 = time.perf_counter() - t0
-    # grow while the predicted time stays inside the budget (CPU MSM cost is ~linear in n)
-    target = logn
-    while target < 22 and t16 * (1 << (target + 1 - 16)) * 2 < budget_s:
+def cpu_baseline_and_parity(ib, ref, budget_s=20.0):
+    """Reference CPU backend on a bounded sample sized to ~10-20 s of CPU work; the SAME bytes then go through the GPU (host
+    pointers -> the plugin-facing path) and the two results are compared as group elements."""
+    import common
+    if ref is None:
+        return {"value": None, "unit": "points/s", "cores": os.cpu_count(), "kind": "reference", "sample": "unavailable: oracle/_ref/bn254 not present"}, None
+    ref.set_device("CPU", 0)
+    n16 = 1 << 16
+    s, P = common.seeded_scalars("bn254_fr", n16, 16), common.tiled_g1_points("bn254", n16, 1 << 14, 17)
+    ref.msm(s, P, n16)
+    t0 = time.perf_counter(); ref.msm(s, P, n16); t16 = time.perf_counter() - t0
+    target = 16
+    while target < 22 and t16 * (1 << (target + 1 - 16)) * 2 < budget_s:  # CPU MSM cost is ~linear in n
         target += 1
     n = 1 << target
-    s, P = r.generate_scalars(n), r.generate_affine_points(n)
-    t0 = time.perf_counter(); r.msm(s, P, n); t1 = time.perf_counter() - t0
-    t0 = time.perf_counter(); r.msm(s, P, n); t2 = time.perf_counter() - t0
+    s, P = common.seeded_scalars("bn254_fr", n, 1600 + target), common.tiled_g1_points("bn254", n, 1 << 14, 1700 + target)
+    t0 = time.perf_counter(); exp = ref.msm(s, P, n); t1 = time.perf_counter() - t0
+    t0 = time.perf_counter(); ref.msm(s, P, n); t2 = time.perf_counter() - t0
     t = min(t1, t2)
-    return {"value": n / t, "unit": "points/s", "cores": os.cpu_count(), "kind": "reference",
-            "sample": f"icicle CPU backend (oracle/_ref built from /root/reference sources, g++ -O3, Taskflow stand-in), BN254 G1 MSM 2^{target} points, best of 2 ({t:.2f} s)"}
+    got = ib.msm(ib.Curve.BN254_G1, s, P, n)
+    ok = bool(ref.projective_eq(got[0], exp[0]))
+    cpu = {"value": n / t, "unit": "points/s", "cores": os.cpu_count(), "kind": "reference",
+           "sample": f"{CPU_NOTE}; BN254 G1 MSM 2^{target} points (seeded scalars, 2^14 distinct points tiled), best of 2 ({t1:.2f} s, {t2:.2f} s)"}
+    return cpu, {"what": "GPU (host-pointer path) == reference CPU backend on identical bytes, projective_eq", "logn": target, "ok": ok}
 
 
 def main():
@@ -196,6 +234,27 @@ def emit(fd, line):
     os.write(fd, (json.dumps(line) + "\n").encode())
 
 
+def timed(torch, dist, world, dev, fn, steps, warmup=1):
+    """barrier + sync, `steps` calls of fn bracketed by CUDA events on the current stream, barrier + sync; max over ranks -> ms/step"""
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / steps
+
+
 def _main(out_fd):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -209,6 +268,7 @@ def _main(out_fd):
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ntt", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 4/5 and the strong-scaling line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -223,6 +283,7 @@ def _main(out_fd):
     import torch
     import torch.distributed as dist
     import icicle_b200 as ib  # raises ImportError if the native library is missing: no fallback
+    import common
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (the product has no CPU path)")
@@ -241,12 +302,15 @@ def _main(out_fd):
     total_out = ib.device_empty(24, dev).view(1, 24)
     c_used = args.c or ib.msm_choose_c(CURVE, n)
 
+    def combine(res):
+        # the single exchange step of a point-sharded MSM: all-gather 96 B per rank over NVLink, then one EC-sum kernel
+        dist.all_gather_into_tensor(gathered.view(-1), res.view(-1))
+        ib.ec_sum(CURVE, gathered, world, ib.VecOpsConfig(is_async=True), total_out)
+
     def step_device():
         ib.msm(CURVE, scalars, points, n, ib.MSMConfig(c=args.c, is_async=True), result)
         if world > 1:
-            # the single exchange step of a point-sharded MSM: all-gather 96 B per rank over NVLink, then one EC-sum kernel
-            dist.all_gather_into_tensor(gathered.view(-1), result.view(-1))
-            ib.ec_sum(CURVE, gathered, world, ib.VecOpsConfig(is_async=True), total_out)
+            combine(result)
 
     def barrier():
         if world > 1:
@@ -276,7 +340,7 @@ def _main(out_fd):
     ms_step = float(t.item()) / args.steps
     value = world * n / (ms_step * 1e-3)
 
-    # ---- roofline of the dominant kernel: CUDA events around k_accumulate inside the call ----------------------------------
+    # ---- roofline of the dominant stage: CUDA events around the bucket accumulation inside the call ----------------------------
     ib.set_profiling(True)
     acc_ms, stage_sum = [], {}
     for _ in range(3):
@@ -302,89 +366,292 @@ def _main(out_fd):
                 "imad_frac": (n * nwin * prod_per_entry * 140 / (acc * 1e-3)) / IMAD_WIDE_PEAK,
                 "note": "integer-multiply bound: imad_frac = (N * windows * products/entry * 140 IMAD.WIDE) / stage time vs the measured 9.26e12 IMAD.WIDE/s"}
 
-    # ---- e2e: host (pinned) buffers through the C ABI; H2D + D2H inside the timed region -----------------------------------
+    ref = load_reference("bn254") if rank == 0 or not args.no_e2e else None
+    have_frontend = (not args.no_e2e) and load_frontend_cuda(ref, local_rank)
+
+    # ---- e2e: host buffers through the plugin call; H2D + D2H inside the timed region --------------------------------------------
     e2e = None
     if not args.no_e2e:
-        h_s, p1 = pinned_array(ib, (n, 8))
-        h_p, p2 = pinned_array(ib, (n, 16))
-        ib.capi.check(ib.capi.lib.b200_copy_to_host(h_s.ctypes.data, scalars.data_ptr(), h_s.nbytes, None, 0), "d2h")
-        ib.capi.check(ib.capi.lib.b200_copy_to_host(h_p.ctypes.data, points.data_ptr(), h_p.nbytes, None, 0), "d2h")
+        h_s = ib.to_host(scalars)                      # pageable numpy arrays: what an unmodified caller holds
+        h_p = ib.to_host(points)
         h_res = np.zeros((1, 24), dtype=np.uint32)
-
-        def step_host():
-            ib.msm(CURVE, h_s, h_p, n, ib.MSMConfig(c=args.c), h_res)  # host in, host out: blocking call
-            if world > 1:
-                r_dev = ib.to_device(h_res, dev)
-                dist.all_gather_into_tensor(gathered.view(-1), r_dev.view(-1))
-                ib.ec_sum(CURVE, gathered, world, ib.VecOpsConfig(), total_out)
-
-        step_host()
-        barrier()
         k2 = max(2, min(args.steps, 3))
-        t0 = time.perf_counter()
-        e0.record()
-        for _ in range(k2):
-            step_host()
-        e1.record()
-        barrier()
-        ms2 = e0.elapsed_time(e1)
-        t2 = torch.tensor([ms2], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        ms2 = float(t2.item()) / k2
-        e2e = {"value": world * n / (ms2 * 1e-3), "unit": "points/s", "h2d_bytes_per_step": ALG_BYTES_PER_POINT * n, "d2h_bytes_per_step": 96,
-               "ms_per_step": ms2, "steps": k2}
+        variants = {}
+
+        def finish_multi():
+            if world > 1:
+                combine(ib.to_device(h_res, dev))
+                torch.cuda.synchronize()
+
+        def run_variant(name, call):
+            def one():
+                call()
+                finish_multi()
+            ms = timed(torch, dist, world, dev, one, k2, warmup=1)
+            variants[name] = {"value": world * n / (ms * 1e-3), "ms_per_step": ms}
+
+        def cabi_pageable():
+            ib.msm(CURVE, h_s, h_p, n, ib.MSMConfig(c=args.c), h_res)   # host in, host out: blocking call
+        run_variant("cabi_pageable", cabi_pageable)
+        if have_frontend:
+            def frontend_pageable():
+                ref.set_device("CUDA", local_rank)
+                h_res[:] = ref.msm(h_s, h_p, n, c=args.c)
+            run_variant("frontend_pageable", frontend_pageable)
+            ref.set_device("CPU", 0)
+        p_s, p1 = pinned_array(ib, (n, 8))
+        p_p, p2 = pinned_array(ib, (n, 16))
+        p_s[:] = h_s
+        p_p[:] = h_p
+
+        def cabi_pinned():
+            ib.msm(CURVE, p_s, p_p, n, ib.MSMConfig(c=args.c), h_res)
+        run_variant("cabi_pinned", cabi_pinned)
         ib.capi.lib.b200_host_free_pinned(p1)
         ib.capi.lib.b200_host_free_pinned(p2)
-        del h_s, h_p
+        head = "frontend_pageable" if "frontend_pageable" in variants else "cabi_pageable"
+        e2e = {"value": variants[head]["value"], "unit": "points/s", "h2d_bytes_per_step": ALG_BYTES_PER_POINT * n, "d2h_bytes_per_step": 96,
+               "ms_per_step": variants[head]["ms_per_step"], "steps": k2, "path": head,
+               "path_note": ("unmodified reference frontend bn254_msm with Device{CUDA} -> dispatcher -> registration shim -> C ABI, pageable host vectors"
+                             if head == "frontend_pageable" else "C ABI b200_msm with pageable host vectors (reference frontend build not present)"),
+               "variants": variants}
+        del h_s, h_p, p_s, p_p
+
+    # ---- the other BASELINE configs, sharded by batch index / point range over the ranks ----------------------------------------
+    configs = None
+    if not args.no_configs:
+        del points
+        torch.cuda.empty_cache()
+        ib.trim_scratch(0)
+        configs = run_configs(torch, dist, ib, common, args, rank, world, dev, peak, scalars, combine if world > 1 else None)
 
     # ---- secondary metric: BN254 NTT elements/s @ 2^ntt_logn (N = 1 only) ----------------------------------------------------
     ntt = None
     if not args.no_ntt and world == 1:
-        del points
+        points = None
         torch.cuda.empty_cache()
-        from icicle_b200 import utils
-        fp = utils.field_params("bn254_fr")
-        F = ib.Field.BN254_FR
-        nl = args.ntt_logn
-        ib.ntt_init_domain(F, utils.to_limbs([pow(fp["rou"], 1 << (fp["two_adicity"] - nl), fp["p"])], 8)[0])
-        x = scalars[: 1 << nl].contiguous() if nl <= args.logn else synth_inputs(torch, ib, nl, 7, dev)[0]
-        y = ib.device_empty((1 << nl) * 8, dev)
-        out = {}
-        for nm, d in (("forward", ib.NTTDir.kForward), ("inverse", ib.NTTDir.kInverse)):
-            for _ in range(3):
-                ib.ntt(F, x, 1 << nl, d, ib.NTTConfig(is_async=True), y)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(args.steps):
-                ib.ntt(F, x, 1 << nl, d, ib.NTTConfig(is_async=True), y)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / args.steps
-            out[nm] = {"elements_per_s": (1 << nl) / (ms * 1e-3), "ms": ms}
-        a = ALG_BYTES_PER_NTT_ELEM * (1 << nl) / (out["forward"]["ms"] * 1e-3) / 1e9
-        ntt = {"metric": "bn254_ntt_elements_per_s", "logn": nl, "ordering": "kNN", **out,
-               "roofline": {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": NCU_NTT_TRAFFIC_BYTES.get(nl),
-                            "kernel": "k_ntt_tile<Fp<bn254_fr>> x 3 passes (IMAD.WIDE bound: sm 62-69 %, dram 9-12 %, profiles/r1_ncu_ntt_passes.txt)"}}
-        ib.ntt_release_domain(F)
+        ntt = run_ntt_secondary(torch, ib, common, args, dev, peak, scalars, ref if rank == 0 else None, have_frontend)
 
-    cpu = None
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline()
+        cpu, parity = cpu_baseline_and_parity(ib, ref)
 
     if rank == 0:
         line = {
             "metric": "bn254_g1_msm_points_per_s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (254-bit modular integers, Montgomery arithmetic in IMAD.WIDE chains)",
-            "data": "synthetic: uniform scalars < p; 2^16 distinct BN254 G1 points tiled to N; device-resident for `value`, pinned host for `e2e`",
+            "data": "synthetic: uniform scalars < p; 2^16 distinct BN254 G1 points tiled to N; device-resident for `value`, host (pageable / pinned) for `e2e`",
             "config": {"workload": f"BN254 G1 MSM 2^{args.logn} per GPU (BASELINE configs[1]), precompute_factor 1, window c={c_used}",
                        "l2": "inputs (6 GiB at 2^26) exceed the 126 MB L2, no flush needed", "multi_gpu": "point-sharded; one NCCL all-gather of 96 B partials + ec_sum kernel"},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "secondary": ntt,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "parity_checked": parity,
+            "secondary": ntt, "configs": configs,
         }
         emit(out_fd, line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_ntt_secondary(torch, ib, common, args, dev, peak, scalars, ref, have_frontend):
+    from icicle_b200 import utils
+    fp = utils.field_params("bn254_fr")
+    F = ib.Field.BN254_FR
+    nl = args.ntt_logn
+    nn = 1 << nl
+    root = utils.to_limbs([pow(fp["rou"], 1 << (fp["two_adicity"] - nl), fp["p"])], 8)[0]
+    ib.ntt_release_domain(F)
+    ib.ntt_init_domain(F, root)
+    x = scalars[:nn].contiguous() if nl <= args.logn else rand_scalars_dev(torch, nn, 7, dev)
+    y = ib.device_empty(nn * 8, dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = {}
+    for nm, d in (("forward", ib.NTTDir.kForward), ("inverse", ib.NTTDir.kInverse)):
+        for _ in range(3):
+            ib.ntt(F, x, nn, d, ib.NTTConfig(is_async=True), y)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            ib.ntt(F, x, nn, d, ib.NTTConfig(is_async=True), y)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out[nm] = {"elements_per_s": nn / (ms * 1e-3), "ms": ms}
+    a = ALG_BYTES_PER_NTT_ELEM * nn / (out["forward"]["ms"] * 1e-3) / 1e9
+    ntt = {"metric": "bn254_ntt_elements_per_s", "logn": nl, "ordering": "kNN", **out,
+           "roofline": {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": NCU_NTT_TRAFFIC_BYTES.get(nl),
+                        "kernel": "k_ntt_tile<Fp<bn254_fr>> passes (IMAD.WIDE bound)"}}
+    # e2e: host vectors in and out through the plugin call (H2D + D2H of 32 B/element each way inside the timed region)
+    hx = ib.to_host(x)
+    variants = {}
+
+    def t_host(fn, k=3):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / k * 1e3
+    ms = t_host(lambda: ib.ntt(F, hx, nn, ib.NTTDir.kForward))
+    variants["cabi_pageable"] = {"value": nn / (ms * 1e-3), "ms_per_step": ms}
+    if have_frontend and ref is not None:
+        ref.set_device("CUDA", dev.index or 0)
+        ref.ntt_release_domain()
+        ref.ntt_init_domain(root)
+        ms = t_host(lambda: ref.ntt(hx, nn, 0))
+        variants["frontend_pageable"] = {"value": nn / (ms * 1e-3), "ms_per_step": ms}
+        ref.ntt_release_domain()
+        ref.set_device("CPU", 0)
+    head = "frontend_pageable" if "frontend_pageable" in variants else "cabi_pageable"
+    ntt["e2e"] = {"value": variants[head]["value"], "unit": "elements/s", "h2d_bytes_per_step": 32 * nn, "d2h_bytes_per_step": 32 * nn,
+                  "ms_per_step": variants[head]["ms_per_step"], "path": head, "variants": variants}
+    # CPU baseline on a bounded sample + parity on identical bytes
+    if ref is not None and not args.no_cpu_baseline:
+        sl = min(nl, 22)
+        sn = 1 << sl
+        ref.set_device("CPU", 0)
+        ref.ntt_release_domain()
+        ref.ntt_init_domain(root)
+        hs = hx[:sn]
+        ref.ntt(hs, sn, 0)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter(); exp = ref.ntt(hs, sn, 0); ts.append(time.perf_counter() - t0)
+        got = ib.ntt(F, hs, sn, ib.NTTDir.kForward)
+        back = ib.ntt(F, exp, sn, ib.NTTDir.kInverse)
+        ref.ntt_release_domain()
+        ntt["cpu_baseline"] = {"value": sn / min(ts), "unit": "elements/s", "cores": os.cpu_count(), "kind": "reference",
+                               "sample": f"{CPU_NOTE}; BN254 forward NTT 2^{sl}, best of 3 ({min(ts):.3f} s)"}
+        ntt["parity_checked"] = {"what": "GPU forward NTT == reference CPU backend (memcmp) and GPU inverse of the reference output == input", "logn": sl,
+                                 "ok": bool(np.array_equal(got, exp) and np.array_equal(back, hs))}
+    ib.ntt_release_domain(F)
+    return ntt
+
+
+def run_configs(torch, dist, ib, common, args, rank, world, dev, peak, scalars, combine):
+    """BASELINE configs 4 and 5 sharded over the ranks (weak in nothing: the TOTAL work is fixed = "strong"), plus strong scaling
+    of one 2^26 BN254 MSM by point range.  Every line: aggregate rate, ms per pass (max over ranks), HBM roofline fraction of the
+    algorithmic bytes, and a parity flag for the check that ran in this process."""
+    from icicle_b200 import utils
+    out = []
+    GOLD = os.path.join(ROOT, "tests", "golden")
+    steps = 2
+
+    def alltrue(flag):
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    # ---- config 4: BLS12-381 G1 and G2 MSM 2^24, batch 8, shared bases: batch index partitioned, no exchange -------------------
+    try:
+        g = np.load(os.path.join(GOLD, "bls12_381.npz"))
+        logn, batch = 24, 8
+        n = 1 << logn
+        lo, hi = ib.shard_range(batch, world, rank)
+        mine = hi - lo
+        for nm, curve, src, alg in (("G1", ib.Curve.BLS12_381_G1, g["msm_points"], 32 * batch + 96), ("G2", ib.Curve.BLS12_381_G2, g["g2_points"], 32 * batch + 192)):
+            if mine == 0:
+                continue
+            base = np.ascontiguousarray(src[[i for i in range(src.shape[0]) if src[i].any()]])  # the reference's own points (no zero point)
+            reps = (1 << 12) // base.shape[0] + 1
+            tile = ib.to_device(np.tile(base, (reps, 1))[: 1 << 12], dev)
+            P = tile.repeat(n >> 12, 1).contiguous()
+            s = rand_scalars_dev(torch, n * mine, 400 + rank, dev, top=0x73EDA753)
+            res = ib.device_empty(mine * ib.projective_limbs(curve), dev).view(mine, -1)
+            cfg = lambda c=0: ib.MSMConfig(batch_size=mine, are_points_shared_in_batch=True, is_async=True, c=c)
+            ms = timed(torch, dist, world, dev, lambda: ib.msm(curve, s, P, n, cfg(), res), steps, warmup=1)
+            # parity that fits a bench: the first MSM of this rank's share recomputed alone with another window size must be the same group element
+            alt = ib.msm(curve, s[:n], P, n, ib.MSMConfig(c=14))
+            same = _same_point(ib, utils, curve, ib.to_host(res[0:1])[0], alt[0]) if hasattr(alt, "shape") else False
+            rate = batch * n / (ms * 1e-3)
+            gbs = alg * n / (ms * 1e-3) / 1e9 / world
+            out.append({"config": f"BLS12-381 {nm} MSM 2^{logn} x batch {batch}, shared bases (BASELINE configs[3]), {mine} MSMs per GPU", "n_gpus": world,
+                        "value": rate, "unit": "points/s", "ms_per_pass": ms, "scaling": "strong",
+                        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                     "note": f"algorithmic bytes = (batch*32 + {alg - 32 * batch}) B per point index, per GPU; integer-multiply bound"},
+                        "parity": {"what": "batched result[0] == the same MSM alone with c=14 (group elements); reference parity at 2^20 in tests/test_gpu_fullsize.py", "ok": alltrue(same)}})
+            del P, s, res
+            torch.cuda.empty_cache()
+            ib.trim_scratch(0)
+    except Exception as e:  # noqa
+        out.append({"config": "BLS12-381 G1+G2 MSM 2^24 x batch 8", "error": repr(e)})
+
+    # ---- config 5: BabyBear NTT 2^27, batch 128 (2-adicity 27: the survey's substitute for "2^28 x 64"), rows partitioned -------
+    try:
+        F = ib.Field.BABYBEAR
+        fp = utils.field_params("babybear")
+        logn, batch = 27, 128
+        n = 1 << logn
+        lo, hi = ib.shard_range(batch, world, rank)
+        mine = hi - lo
+        ib.ntt_release_domain(F)
+        ib.ntt_init_domain(F, utils.to_limbs([pow(fp["rou"], 1 << (fp["two_adicity"] - logn), fp["p"])], 1)[0])
+        chunk = min(mine, 16)   # rows per call: 16 x 512 MiB in + out
+        x = torch.randint(0, fp["p"], (chunk * n,), dtype=torch.int64, device=dev).to(torch.int32).contiguous()
+        y = ib.device_empty(chunk * n, dev)
+
+        def one_pass():
+            for _ in range(0, mine, chunk):
+                ib.ntt(F, x, n, ib.NTTDir.kForward, ib.NTTConfig(batch_size=chunk, is_async=True), y)
+        ms = timed(torch, dist, world, dev, one_pass, steps, warmup=1)
+        back = ib.device_empty(chunk * n, dev)
+        ib.ntt(F, y, n, ib.NTTDir.kInverse, ib.NTTConfig(batch_size=chunk), back)
+        ok = bool(torch.equal(back.view(-1), x.view(-1)))
+        rate = batch * n / (ms * 1e-3)
+        gbs = 8.0 * mine * n / (ms * 1e-3) / 1e9
+        out.append({"config": f"BabyBear NTT 2^{logn} x batch {batch} forward kNN (BASELINE configs[4] with the survey's size substitution), {mine} rows per GPU in calls of {chunk}",
+                    "n_gpus": world, "value": rate, "unit": "elements/s", "ms_per_pass": ms, "scaling": "strong",
+                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "note": "algorithmic bytes = 8 B per element per transform, per GPU"},
+                    "parity": {"what": "inverse(forward(x)) == x bit-exactly on this rank's rows; reference parity at 2^24 x 2 and 2^27 in tests/test_gpu_fullsize.py", "ok": alltrue(ok)}})
+        del x, y, back
+        ib.ntt_release_domain(F)
+        torch.cuda.empty_cache()
+        ib.trim_scratch(0)
+    except Exception as e:  # noqa
+        out.append({"config": "BabyBear NTT 2^27 x batch 128", "error": repr(e)})
+
+    # ---- strong scaling of ONE 2^26 BN254 MSM: the point range is partitioned, partials combined by all-gather + ec_sum ----------
+    if world > 1:
+        try:
+            CURVE = ib.Curve.BN254_G1
+            n = 1 << args.logn
+            lo, hi = ib.shard_range(n, world, rank)
+            m = hi - lo
+            base = ib.to_device(common.gen_g1_points("bn254", 1 << 12, 4242), dev)
+            P = base.repeat((m >> 12) + 1, 1)[:m].contiguous()
+            s = scalars[:m].contiguous()
+            res = ib.device_empty(24, dev).view(1, 24)
+
+            def one():
+                ib.msm(CURVE, s, P, m, ib.MSMConfig(is_async=True), res)
+                combine(res)
+            ms = timed(torch, dist, world, dev, one, 3, warmup=2)
+            out.append({"config": f"BN254 G1 MSM 2^{args.logn} split by point range over {world} GPUs ({m} points per GPU) + NCCL all-gather of 96 B partials + ec_sum",
+                        "n_gpus": world, "value": n / (ms * 1e-3), "unit": "points/s", "ms_per_pass": ms, "scaling": "strong",
+                        "roofline": {"bound": "hbm", "achieved": 96.0 * m / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": 96.0 * m / (ms * 1e-3) / 1e9 / peak}})
+            del P, s
+        except Exception as e:  # noqa
+            out.append({"config": "BN254 G1 MSM 2^26 strong scaling", "error": repr(e)})
+    return out
+
+
+def _same_point(ib, utils, curve, a, b):
+    """projective equality by cross-multiplication on python integers (G1) / Fq2 pairs (G2)"""
+    L = ib.projective_limbs(curve) // 3
+    if curve in (ib.Curve.BLS12_381_G2,):
+        Lq = L // 2
+        q = utils.field_params("bls12_381_fq")["p"]
+        nr = utils.curve_params("bls12_381")["nonresidue"]
+        A = utils.from_limbs(np.asarray(a, dtype=np.uint32).reshape(6, Lq))
+        B = utils.from_limbs(np.asarray(b, dtype=np.uint32).reshape(6, Lq))
+        mul = lambda u, v: ((u[0] * v[0] + nr * u[1] * v[1]) % q, (u[0] * v[1] + u[1] * v[0]) % q)
+        (ax, ay, az), (bx, by, bz) = ((A[0], A[1]), (A[2], A[3]), (A[4], A[5])), ((B[0], B[1]), (B[2], B[3]), (B[4], B[5]))
+        return mul(ax, bz) == mul(bx, az) and mul(ay, bz) == mul(by, az)
+    q = utils.field_params("bls12_381_fq")["p"]
+    ax, ay, az = utils.from_limbs(np.asarray(a, dtype=np.uint32).reshape(3, L))
+    bx, by, bz = utils.from_limbs(np.asarray(b, dtype=np.uint32).reshape(3, L))
+    return (ax * bz - bx * az) % q == 0 and (ay * bz - by * az) % q == 0
 
 
 if __name__ == "__main__":

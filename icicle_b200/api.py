@@ -105,6 +105,16 @@ def _ptr(x):
     return a.ctypes.data, False, a
 
 
+def _out_ptr(x):
+    """(pointer, on_device, keepalive) of an OUTPUT buffer: never copied -- a non-contiguous or non-32-bit array would make the
+    kernel write into a temporary and leave the caller's array untouched, so it is rejected instead."""
+    if _is_torch(x):
+        return _ptr(x)
+    if not isinstance(x, np.ndarray) or not x.flags.c_contiguous or not x.flags.writeable or x.dtype.itemsize != 4:
+        raise ValueError("output buffers must be writeable C-contiguous numpy arrays of a 32-bit dtype (uint32 limbs)")
+    return x.ctypes.data, False, x
+
+
 def _stream_handle(stream):
     if stream is None:
         return None
@@ -198,7 +208,7 @@ def msm(curve, scalars, bases, msm_size, config=None, results=None):
             results = device_empty(cfg.batch_size * projective_limbs(curve)).view(cfg.batch_size, -1)
         else:
             results = np.zeros((cfg.batch_size, projective_limbs(curve)), dtype=np.uint32)
-    rp, r_dev, _kr = _ptr(results)
+    rp, r_dev, _kr = _out_ptr(results)
     cfg.are_results_on_device = r_dev
     c = cfg._c()
     check(lib.b200_msm(int(curve), sp, bp, int(msm_size), C.byref(c), rp), "msm")
@@ -214,7 +224,7 @@ def msm_precompute_bases(curve, bases, nof_bases, config, output=None):
         n = nof_bases * cfg.precompute_factor
         output = (device_empty(n * affine_limbs(curve)).view(n, -1) if cfg.are_results_on_device
                   else np.zeros((n, affine_limbs(curve)), dtype=np.uint32))
-    op, o_dev, _ko = _ptr(output)
+    op, o_dev, _ko = _out_ptr(output)
     cfg.are_results_on_device = o_dev
     c = cfg._c()
     check(lib.b200_msm_precompute_bases(int(curve), bp, int(nof_bases), C.byref(c), op), "msm_precompute_bases")
@@ -238,6 +248,52 @@ def msm_pair_levels(curve, msm_size, c=0, config=None):
     """Number of batched-affine pair levels the MSM schedule will run for this size (planning query)."""
     cfg = (config or MSMConfig(c=c))._c()
     return lib.b200_msm_pair_levels(int(curve), int(msm_size), C.byref(cfg))
+
+
+# ---- multi-GPU (SURVEY 8e): one host thread per device inside the backend, or one process per GPU with the same shard arithmetic ---
+def shard_range(total, parts, index):
+    """[lo, hi) of `total` units for part `index` of `parts` (b200_shard_range: sizes differ by at most one, earlier parts
+    take the extras) -- the split b200_msm_multi_gpu / b200_ntt_multi_gpu use per device and bench.py uses per rank."""
+    b, c = C.c_uint64(0), C.c_uint64(0)
+    lib.b200_shard_range(int(total), int(parts), int(index), C.byref(b), C.byref(c))
+    return b.value, b.value + c.value
+
+
+def _device_ids(n_devices, device_ids):
+    if device_ids is None:
+        return int(n_devices), None
+    arr = (C.c_int * len(device_ids))(*[int(d) for d in device_ids])
+    return len(device_ids), arr
+
+
+def msm_multi_gpu(curve, scalars, bases, msm_size, config=None, results=None, n_devices=0, device_ids=None):
+    """b200_msm_multi_gpu: host-resident scalars / bases / results sharded over the devices (batch index, or point range for a
+    single MSM); what the shim calls when MSMConfig.ext carries "multi_gpu"."""
+    cfg = copy.copy(config) if config else MSMConfig()
+    sp, s_dev, _ks = _ptr(scalars)
+    bp, b_dev, _kb = _ptr(bases)
+    if results is None:
+        results = np.zeros((cfg.batch_size, projective_limbs(curve)), dtype=np.uint32)
+    rp, r_dev, _kr = _out_ptr(results)
+    cfg.are_scalars_on_device, cfg.are_points_on_device, cfg.are_results_on_device = s_dev, b_dev, r_dev
+    n, ids = _device_ids(n_devices, device_ids)
+    c = cfg._c()
+    check(lib.b200_msm_multi_gpu(int(curve), sp, bp, int(msm_size), C.byref(c), rp, n, ids), "msm_multi_gpu")
+    return results
+
+
+def ntt_multi_gpu(field, input, size, direction, config=None, output=None, n_devices=0, device_ids=None):
+    """b200_ntt_multi_gpu: a row batch of NTTs sharded by batch index over the devices (host-resident data)."""
+    cfg = copy.copy(config) if config else NTTConfig()
+    ip, i_dev, _ki = _ptr(input)
+    if output is None:
+        output = np.zeros((size * cfg.batch_size, field_limbs(field)), dtype=np.uint32)
+    op, o_dev, _ko = _out_ptr(output)
+    cfg.are_inputs_on_device, cfg.are_outputs_on_device = i_dev, o_dev
+    n, ids = _device_ids(n_devices, device_ids)
+    c = cfg._c()
+    check(lib.b200_ntt_multi_gpu(int(field), ip, int(size), int(direction), C.byref(c), op, n, ids), "ntt_multi_gpu")
+    return output
 
 
 # ---- NTT --------------------------------------------------------------------------------------------------------------
@@ -306,7 +362,7 @@ def ntt(field, input, size, direction, config=None, output=None):
     if output is None:
         n = size * cfg.batch_size * field_limbs(field)
         output = device_empty(n) if cfg.are_outputs_on_device else np.zeros((size * cfg.batch_size, field_limbs(field)), dtype=np.uint32)
-    op, o_dev, _ko = _ptr(output)
+    op, o_dev, _ko = _out_ptr(output)
     cfg.are_outputs_on_device = o_dev
     c = cfg._c()
     check(lib.b200_ntt(int(field), ip, int(size), int(direction), C.byref(c), op), "ntt")
@@ -327,7 +383,7 @@ def ntt_extension(field, input, size, direction, config=None, output=None):
     if output is None:
         n = size * cfg.batch_size * w
         output = device_empty(n) if cfg.are_outputs_on_device else np.zeros((size * cfg.batch_size, w), dtype=np.uint32)
-    op, o_dev, _ko = _ptr(output)
+    op, o_dev, _ko = _out_ptr(output)
     cfg.are_outputs_on_device = o_dev
     c = cfg._c()
     check(lib.b200_ntt_extension(int(field), ip, int(size), int(direction), C.byref(c), op), "ntt_extension")
@@ -345,7 +401,7 @@ def ecntt(curve, input, size, direction, config=None, output=None):
     if output is None:
         n = size * cfg.batch_size * w
         output = device_empty(n) if cfg.are_outputs_on_device else np.zeros((size * cfg.batch_size, w), dtype=np.uint32)
-    op, o_dev, _ko = _ptr(output)
+    op, o_dev, _ko = _out_ptr(output)
     cfg.are_outputs_on_device = o_dev
     c = cfg._c()
     check(lib.b200_ecntt(int(curve), ip, int(size), int(direction), C.byref(c), op), "ecntt")
@@ -394,11 +450,12 @@ def _vec2(field, op, a, b, size, config, output):
     bp, b_dev, _kb = _ptr(b)
     cfg.is_a_on_device, cfg.is_b_on_device = a_dev, b_dev
     if op == VecOp.ACCUMULATE:
+        ap, a_dev, _ka = _out_ptr(a)  # a is updated in place
         output, op_ptr = a, ap
     else:
         if output is None:
             output = _out_like(field, size * cfg.batch_size, cfg.is_result_on_device)
-        op_ptr, o_dev, _ko = _ptr(output)
+        op_ptr, o_dev, _ko = _out_ptr(output)
         cfg.is_result_on_device = o_dev
     c = cfg._c()
     check(lib.b200_vec_op(int(field), int(op), ap, bp, int(size), C.byref(c), op_ptr), f"vec_op({VecOp(op).name})")
@@ -440,7 +497,7 @@ def _unary(fn_name, field_or_curve, a, n_out_elems, limbs, config, output, *extr
     if output is None:
         output = (device_empty(n_out_elems * limbs).view(n_out_elems, -1) if cfg.is_result_on_device
                   else np.zeros((n_out_elems, limbs), dtype=np.uint32))
-    op, o_dev, _ko = _ptr(output)
+    op, o_dev, _ko = _out_ptr(output)
     cfg.is_result_on_device = o_dev
     c = cfg._c()
     fn = getattr(lib, fn_name)
@@ -461,7 +518,7 @@ def vector_div(field, a, b, size, config=None, output=None):
     cfg.is_a_on_device, cfg.is_b_on_device = a_dev, b_dev
     if output is None:
         output = _out_like(field, size * cfg.batch_size, cfg.is_result_on_device)
-    op, o_dev, _ko = _ptr(output)
+    op, o_dev, _ko = _out_ptr(output)
     cfg.is_result_on_device = o_dev
     c = cfg._c()
     check(lib.b200_vector_div(int(field), ap, bp, int(size), C.byref(c), op), "vector_div")
@@ -500,7 +557,7 @@ def poly_eval(field, coeffs, coeffs_size, domain, domain_size, config=None, outp
     cfg.is_a_on_device, cfg.is_b_on_device = c_dev, d_dev
     if output is None:
         output = _out_like(field, domain_size * cfg.batch_size, cfg.is_result_on_device)
-    op, o_dev, _ko = _ptr(output)
+    op, o_dev, _ko = _out_ptr(output)
     cfg.is_result_on_device = o_dev
     c = cfg._c()
     check(lib.b200_poly_eval(int(field), cp, int(coeffs_size), dp, int(domain_size), C.byref(c), op), "poly_eval")
@@ -561,6 +618,21 @@ def projective_convert_montgomery(curve, a, n, is_into, config=None, output=None
     fn, ap, op, c, output = _unary("b200_projective_convert_montgomery", curve, a, n, projective_limbs(curve), cfg, output)
     check(fn(int(curve), ap, int(n), 1 if is_into else 0, C.byref(c), op), "projective_convert_montgomery")
     return output
+
+
+# ---- developer knobs / memory -------------------------------------------------------------------------------------------
+def set_tuning(name, value):
+    """b200_set_tuning: developer / test knob (see include/icicle_b200.h); value None or < 0 restores the built-in policy."""
+    check(lib.b200_set_tuning(name.encode(), -1 if value is None else int(value)), f"set_tuning({name})")
+
+
+def get_tuning(name):
+    return int(lib.b200_get_tuning(name.encode()))
+
+
+def trim_scratch(keep_bytes=0):
+    """Return the library's retained scratch (private stream-ordered pool of the current device) to the driver."""
+    check(lib.b200_trim_scratch(int(keep_bytes)), "trim_scratch")
 
 
 # ---- instrumentation ----------------------------------------------------------------------------------------------------

@@ -23,6 +23,21 @@ namespace b200 {
 
 static inline int map_alloc_error(cudaError_t e) { return e == cudaErrorMemoryAllocation ? B200_OUT_OF_MEMORY : B200_ALLOCATION_FAILED; }
 
+// ---- tuning knobs (developer / test hooks) -------------------------------------------------------------------------------
+// Read ONCE from the environment (B200_<NAME>) when the library is loaded and changeable afterwards only through
+// b200_set_tuning(); the hot path never calls getenv().  -1 = unset (use the built-in policy).
+enum Tune : int {
+  T_MSM_PAIR_LEVELS = 0, T_MSM_CHUNK_TARGET, T_MSM_NO_WIDE_LOADS, T_MSM_PIPELINE_MIN, T_MSM_PIPELINE_CHUNKS, T_MSM_NO_PIPELINE,
+  T_MSM_STAGING_MB, T_MSM_SORT, T_NTT_GEOM, T_NTT31_OFF, T_NTT_COLUMNS_STRIDED, T_NTT_MAXR, T_NTT_TILES, T_NTT_MAXS, T_NTT31_TWO_PASS,
+  T_COUNT
+};
+int tune(Tune k);
+
+// Private stream-ordered memory pool of the current device for the library's temporaries.  The process-wide default pool
+// and device limits are left untouched; freed scratch is retained in OUR pool between calls (MSM / NTT temporaries are
+// re-used call after call) up to B200_SCRATCH_RETAIN_MB (default: everything) and b200_trim_scratch() hands it back.
+cudaMemPool_t scratch_pool();
+
 // Stream-ordered scratch allocation that frees itself (cudaFreeAsync on the same stream) when it goes out of scope.
 struct Scratch {
   void* p = nullptr;
@@ -30,39 +45,16 @@ struct Scratch {
   Scratch() = default;
   Scratch(const Scratch&) = delete;
   Scratch& operator=(const Scratch&) = delete;
-  // Keep freed scratch in the device's default pool (MSM / NTT temporaries are re-used call after call); without this the
-  // pool hands memory back to the driver at every synchronisation and each call pays the allocation again.
-  static void ensure_pool_configured()
-  {
-    static thread_local unsigned long long configured_mask = 0;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
-    if (configured_mask & (1ull << dev)) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t thresh = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
-    }
-    // The MSM gathers 32/64-byte points at random; with the default L2 fetch granularity every gather pulls a whole 128-byte
-    // line from HBM (measured with ncu: 2x the algorithmic bytes).  Ask for sector-granular fills; streaming kernels
-    // request whole lines anyway and are unaffected.
-    {
-      size_t gran = 32;
-      if (const char* ev = getenv("B200_L2_FETCH")) gran = (size_t)atoi(ev);
-      if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
-    }
-    configured_mask |= (1ull << dev);
-  }
   int alloc(size_t bytes, cudaStream_t stream)
   {
     release();
-    ensure_pool_configured();
     s = stream;
     if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+    cudaMemPool_t pool = scratch_pool();
+    cudaError_t e = pool ? cudaMallocFromPoolAsync(&p, bytes, pool, stream) : cudaMallocAsync(&p, bytes, stream);
     if (e != cudaSuccess) {
       p = nullptr;
-      fprintf(stderr, "[icicle_b200] cudaMallocAsync(%zu) failed: %s\n", bytes, cudaGetErrorString(e));
+      fprintf(stderr, "[icicle_b200] scratch allocation of %zu bytes failed: %s\n", bytes, cudaGetErrorString(e));
       (void)cudaGetLastError();
       return map_alloc_error(e);
     }
@@ -78,23 +70,41 @@ struct Scratch {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-// Input staging: returns a device pointer for `src`; copies through `buf` if `src` is host memory.
+// The reference's are_*_on_device flags are hints that wrappers do not always set (the Rust precompute_bases passes a
+// DeviceSlice with the flag left false): trust a `true` flag, otherwise ask the driver what the pointer is.
+static inline bool ptr_on_device(const void* p, bool flag)
+{
+  if (flag) return true;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+// kernels access field elements with 128-bit loads; storage<N> only promises 4-byte alignment (math/storage.h:4-9)
+static inline bool misaligned16(const void* p) { return (((uintptr_t)p) & 15u) != 0; }
+
+// Input staging: returns a device pointer for `src`; copies through `buf` if `src` is host memory (or a device pointer
+// that is not 16-byte aligned).
 static inline int stage_in(const void*& dev_ptr, const void* src, size_t bytes, bool on_device, cudaStream_t s, Scratch& buf)
 {
-  if (on_device) {
+  on_device = ptr_on_device(src, on_device);
+  if (on_device && !misaligned16(src)) {
     dev_ptr = src;
     return B200_SUCCESS;
   }
   int err = buf.alloc(bytes, s);
   if (err) return err;
-  B200_CUDA_TRY(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, s), B200_COPY_FAILED);
+  B200_CUDA_TRY(cudaMemcpyAsync(buf.p, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), B200_COPY_FAILED);
   dev_ptr = buf.p;
   return B200_SUCCESS;
 }
-// Output staging: a device pointer to write results into (the user's if on device, scratch otherwise).
+// Output staging: a device pointer to write results into (the user's if on device and aligned, scratch otherwise).
 static inline int stage_out(void*& dev_ptr, void* dst, size_t bytes, bool on_device, cudaStream_t s, Scratch& buf)
 {
-  if (on_device) {
+  on_device = ptr_on_device(dst, on_device);
+  if (on_device && !misaligned16(dst)) {
     dev_ptr = dst;
     return B200_SUCCESS;
   }
@@ -103,16 +113,14 @@ static inline int stage_out(void*& dev_ptr, void* dst, size_t bytes, bool on_dev
   dev_ptr = buf.p;
   return B200_SUCCESS;
 }
-// Finish: copy results back if they live on the host; block unless (async and results on device).
+// Finish: copy results back if they were staged; block unless (async and results on device).
 // Matches the reference contract "results to host force a sync even if is_async" (icicle/include/icicle/msm.h:45-51).
 static inline int finish_out(void* dst, const void* dev_ptr, size_t bytes, bool on_device, bool is_async, cudaStream_t s)
 {
-  if (!on_device) {
-    B200_CUDA_TRY(cudaMemcpyAsync(dst, dev_ptr, bytes, cudaMemcpyDeviceToHost, s), B200_COPY_FAILED);
-    B200_CUDA_TRY(cudaStreamSynchronize(s), B200_SYNCHRONIZATION_FAILED);
-  } else if (!is_async) {
-    B200_CUDA_TRY(cudaStreamSynchronize(s), B200_SYNCHRONIZATION_FAILED);
-  }
+  on_device = ptr_on_device(dst, on_device);
+  if (dst != dev_ptr)
+    B200_CUDA_TRY(cudaMemcpyAsync(dst, dev_ptr, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s), B200_COPY_FAILED);
+  if (!on_device || !is_async) B200_CUDA_TRY(cudaStreamSynchronize(s), B200_SYNCHRONIZATION_FAILED);
   return B200_SUCCESS;
 }
 
@@ -132,6 +140,7 @@ struct StageTimer {
   void begin(cudaStream_t stream);
   void mark(const char* name);
   void finish(const char* what);
+  ~StageTimer(); // destroys the events of a call that returned early
 };
 
 static inline int num_sms()

@@ -3,11 +3,14 @@
 // Replaces (on device) what the reference computes on the host with Barrett reduction:
 //   icicle/include/icicle/math/modular_arithmetic.h:354-406 (add/sub/mul), :583-597 (Montgomery conversion, neg)
 //   icicle/include/icicle/math/host_math.h:209-238,437-470 (multiply_raw, Barrett)
-// The reference's device branch includes headers that are not in its tree (modular_arithmetic.h:4-7), so this is a
-// from-scratch design: values are N little-endian u32 limbs (the reference's `storage<N>` layout, math/storage.h:36-48);
+// The reference's device branch includes headers that are not in its tree (modular_arithmetic.h:4-7), so nothing here comes
+// from the reference: values are N little-endian u32 limbs (the reference's `storage<N>` layout, math/storage.h:36-48);
 // multiplication is Montgomery (R = 2^(32N), the same R the reference uses for its *_montgomery_form flags,
 // fields/params_gen.h:35-50) written as even/odd-column carry chains so that every `mad.lo.cc/madc.hi.cc` pair
 // becomes one IMAD.WIDE.U32.X in SASS (B200 has no 64-bit integer multiplier; IMAD.WIDE.U32 is the widest).
+// CREDIT: the even/odd-column Montgomery multiplier (mad_n_redc / cmad_n / madc_n_rshift below, their structure and names)
+// is the public algorithm of Supranational's sppark (ff/mont_t.cuh, Apache-2.0), restated here for this code base's Fp<>
+// type and host emulation; the dedicated squaring (sqr_impl) is derived from it.
 //
 // All inputs/outputs of add/sub/mul are fully reduced, i.e. in [0, p).  Kernels keep data in the reference's canonical
 // standard form at the API boundary and use the identity  mont_mul(x, y*R) = x*y  to avoid conversions where possible.
@@ -342,8 +345,9 @@ struct Fp {
   B200_HD Fp from_mont() const { return mont_mul(*this, raw_one()); }
 };
 
-// 128-bit vectorised global memory access for N % 4 == 0, 32-bit otherwise.  `aligned16` must be true only when the
-// pointer is 16-byte aligned (user host buffers are only guaranteed 4-byte alignment: math/storage.h:4-9).
+// 128-bit vectorised global memory access for N % 4 == 0, 32-bit otherwise.  The pointer must be 16-byte aligned: the host
+// side guarantees it (stage_in / stage_out in common.cuh copy caller DEVICE buffers that are only 4-byte aligned -- all
+// that storage<N> promises, math/storage.h:4-9 -- through aligned scratch; staging areas are cudaMalloc-aligned).
 template <class F>
 B200_D F load_fp(const uint32_t* p)
 {

@@ -37,6 +37,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
+#include <memory>
+#include <thread>
+#include <vector>
 
 namespace b200 { namespace msm {
 
@@ -440,7 +444,7 @@ inline int batch_chunk(uint32_t n, const MsmPlan& pl, int batch, bool shared, co
   const uint64_t ent_per_msm = (uint64_t)n * pl.nwin;
   const uint64_t max_entries = 1ull << 30;
   int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)batch, max_entries / std::max<uint64_t>(ent_per_msm, 1)));
-  if (cfg->ext_nof_chunks > 0) chunk = std::max(1, (batch + cfg->ext_nof_chunks - 1) / cfg->ext_nof_chunks);
+  if (cfg->ext_nof_chunks > 0) chunk = std::min(chunk, std::max(1, (batch + cfg->ext_nof_chunks - 1) / cfg->ext_nof_chunks)); // never above the 2^30-entry cap
   if (!shared) { // point indices must fit 31 bits
     while (chunk > 1 && (uint64_t)chunk * n * pl.pf >= (1ull << 31)) chunk--;
   }
@@ -458,7 +462,7 @@ inline int choose_pair_levels(uint64_t max_ent, uint64_t max_buckets)
   if (max_ent >= (1ull << 26) && avg_run >= 8.0) {
     while ((8 << levels) <= avg_run && levels < 5) levels++;
   }
-  if (const char* ev = getenv("B200_MSM_PAIR_LEVELS")) levels = std::max(0, std::min(8, atoi(ev)));
+  if (tune(T_MSM_PAIR_LEVELS) >= 0) levels = std::min(8, tune(T_MSM_PAIR_LEVELS));
   return levels;
 }
 
@@ -493,7 +497,7 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
 
   // chunk length for the bucket reduction: >= 64K threads if possible
   int chunk_target = 16; // log2 of the thread count k_bucket_chunks aims for
-  if (const char* ev = getenv("B200_MSM_CHUNK_TARGET")) chunk_target = std::max(10, std::min(22, atoi(ev)));
+  if (tune(T_MSM_CHUNK_TARGET) >= 0) chunk_target = std::max(10, std::min(22, tune(T_MSM_CHUNK_TARGET)));
   int chunk_log = std::max(0, std::min(7, (pl.c - 1 + ilog2_ceil(max_modules)) - chunk_target));
   if (chunk_log > pl.c - 1) chunk_log = pl.c - 1;
   const uint64_t max_chunks = max_buckets >> chunk_log;
@@ -581,7 +585,7 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
     const uint32_t sentinel = (uint32_t)n_buckets;
     const uint32_t* sc = (const uint32_t*)d_scal + (uint64_t)b0 * n * S::N;
     const uint32_t* pts = pts_m + (shared ? 0 : (uint64_t)b0 * n * pl.pf * AW);
-    const bool pts_wide = (((uintptr_t)pts) & 31u) == 0 && (F::BYTES % 32 == 0) && !getenv("B200_MSM_NO_WIDE_LOADS");
+    const bool pts_wide = (((uintptr_t)pts) & 31u) == 0 && (F::BYTES % 32 == 0) && tune(T_MSM_NO_WIDE_LOADS) <= 0;
 
     if (do_acc) {
     // K6
@@ -742,27 +746,74 @@ __global__ void __launch_bounds__(MSM_THREADS) k_bucket_merge(uint32_t* __restri
   store_xyzz<F>(dst + i * XW, a);
 }
 
-// Host-pointer fast path (the reference-facing call with HOST scalars and points, i.e. what `e2e` measures).  PCIe (~55 GB/s)
-// moves 96 B/point, so a 2^26 MSM is transfer-bound unless the copies hide behind the arithmetic.  The whole input gets a
-// device staging area (as the plain host path would allocate anyway); a private copy stream pushes it up chunk by chunk
-// without ever waiting for the compute stream, and the caller's stream runs digits -> sort -> bucket accumulation of chunk i
-// (MSM_ACC, window size chosen for the WHOLE msm) as soon as chunk i has landed.  Chunk 0 accumulates straight into the
-// running bucket array, later chunks into a second array that k_bucket_merge folds in; the bucket reduction + Horner
-// (MSM_RED) runs once at the end.  Exposed transfer time = the first chunk only.
-inline cudaStream_t copy_stream_for_current_device()
+// ---------------------------------------------------------------------------------------------------------------------
+// Chunked MSM: one MSM processed in point-range chunks that all accumulate into ONE bucket array (window size of the whole
+// MSM); the bucket reduction + Horner run once at the end.  Two users:
+//  * host-pointer calls of >= 2^23 points (the reference-facing call, what `e2e` measures): PCIe moves 96 B/point at ~55 GB/s,
+//    so a 2^26 MSM is transfer-bound unless the copies hide behind the arithmetic.  The whole input gets a device staging
+//    area; copies run ahead on private copy streams and never wait for the compute stream, which processes chunk i as soon as
+//    it has landed.  PINNED sources are copied directly (one cudaMemcpyAsync per chunk and array).  PAGEABLE sources -- what
+//    Rust / Go / C++ callers normally pass -- are moved by a few host copier threads through a ring of pinned slots
+//    (memcpy user -> slot, cudaMemcpyAsync slot -> device), because cudaMemcpyAsync from pageable memory blocks the calling
+//    thread and runs at a fraction of the PCIe rate;
+//  * device-resident calls whose entry list would not fit 32-bit indexing / memory (n * windows > 2^30, i.e. > 2^26 points at
+//    c = 20): no copies, equal chunks.
+// Chunk 0 accumulates straight into the running bucket array, later chunks into a second array that k_bucket_merge folds in.
+// ---------------------------------------------------------------------------------------------------------------------
+struct CopierCtx {
+  cudaStream_t st = nullptr;
+  void* slot[2] = {nullptr, nullptr};
+  cudaEvent_t slot_free[2] = {nullptr, nullptr};
+};
+constexpr size_t COPIER_SLOT_BYTES = 4u << 20;
+
+struct DeviceRes { // per (host thread, device): streams / events / copier contexts reused call after call
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> events;
+  std::vector<CopierCtx*> copiers;
+  cudaEvent_t event(size_t i)
+  {
+    while (events.size() <= i) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      events.push_back(e);
+    }
+    return events[i];
+  }
+  CopierCtx* copier(size_t i)
+  {
+    while (copiers.size() <= i) {
+      CopierCtx* c = new CopierCtx;
+      bool ok = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) == cudaSuccess;
+      for (int k = 0; k < 2 && ok; k++) {
+        ok = cudaHostAlloc(&c->slot[k], COPIER_SLOT_BYTES, cudaHostAllocDefault) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->slot_free[k], cudaEventDisableTiming) == cudaSuccess;
+      }
+      if (!ok) {
+        (void)cudaGetLastError();
+        delete c;
+        return nullptr;
+      }
+      copiers.push_back(c);
+    }
+    return copiers[i];
+  }
+};
+inline DeviceRes* device_res()
 {
-  static thread_local cudaStream_t streams[64] = {};
+  static thread_local DeviceRes res[64];
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return nullptr;
-  if (!streams[dev]) cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking);
-  return streams[dev];
+  DeviceRes* r = &res[dev];
+  if (!r->copy_stream && cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  return r;
 }
 
 // B200_MSM_PIPELINE_MIN=<points> (tests): smallest host-pointer MSM that takes the pipeline, and the chunks may then be small
 inline uint32_t pipeline_min_points()
 {
-  if (const char* ev = getenv("B200_MSM_PIPELINE_MIN")) return (uint32_t)std::max(2, atoi(ev));
+  if (tune(T_MSM_PIPELINE_MIN) >= 0) return (uint32_t)std::max(2, tune(T_MSM_PIPELINE_MIN));
   return 1u << 23;
 }
 
@@ -774,11 +825,11 @@ inline uint32_t pipeline_min_points()
 // forces k equal chunks instead.
 inline uint32_t pipeline_schedule(uint32_t n, uint32_t* sizes, uint32_t max_chunks)
 {
-  const bool tiny_ok = getenv("B200_MSM_PIPELINE_MIN") != nullptr; // tests: allow tiny chunks
+  const bool tiny_ok = tune(T_MSM_PIPELINE_MIN) >= 0; // tests: allow tiny chunks
   const uint32_t min_chunk = tiny_ok ? 1u : (1u << 20);
   uint32_t k = 0, left = n;
-  if (const char* ev = getenv("B200_MSM_PIPELINE_CHUNKS")) {
-    const uint32_t want = (uint32_t)std::max(1, std::min((int)max_chunks, atoi(ev)));
+  if (tune(T_MSM_PIPELINE_CHUNKS) > 0) {
+    const uint32_t want = (uint32_t)std::max(1, std::min((int)max_chunks, tune(T_MSM_PIPELINE_CHUNKS)));
     const uint32_t each = std::max<uint32_t>((n + want - 1) / want, min_chunk);
     while (left > 0 && k < max_chunks) {
       sizes[k] = (k + 1 == max_chunks) ? left : std::min(each, left);
@@ -796,8 +847,129 @@ inline uint32_t pipeline_schedule(uint32_t n, uint32_t* sizes, uint32_t max_chun
   return k;
 }
 
+// largest point count whose entry list (n * windows) stays within 2^30 entries: bigger device-resident MSMs are chunked
+inline uint32_t device_chunk_points(const MsmPlan& pl) { return (uint32_t)std::max<uint64_t>(1, (1ull << 30) / (uint64_t)pl.nwin); }
+
+enum HostKind : int { HK_DEVICE = 0, HK_PINNED = 1, HK_PAGEABLE = 2 };
+inline HostKind host_kind(const void* p, bool flag_on_device)
+{
+  if (flag_on_device) return HK_DEVICE;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return HK_PAGEABLE;
+  }
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return HK_DEVICE;
+  return a.type == cudaMemoryTypeHost ? HK_PINNED : HK_PAGEABLE;
+}
+
+// One array (scalars or points) of a chunked call: where chunk i's slice lives on the device.
+struct ChunkArray {
+  const uint8_t* host = nullptr; // source if it has to be copied
+  uint8_t* dev = nullptr;        // device base (staging area, or the caller's device buffer)
+  size_t elem_bytes = 0;         // bytes per point index
+  HostKind kind = HK_DEVICE;
+};
+
+// Pageable sources: T host threads move the slices through pinned slots.  Thread t owns pieces t, t+T, ... (ordered by chunk)
+// and publishes, per chunk, an event recorded after its last piece of that chunk plus a host-side progress counter, so the
+// calling thread only makes the compute stream wait on events that have really been recorded.
+struct PageableCopy {
+  struct Piece { const uint8_t* src; uint8_t* dst; size_t bytes; uint32_t chunk; };
+  std::vector<Piece> pieces;
+  std::vector<std::thread> threads;
+  std::vector<CopierCtx*> ctx;
+  std::vector<cudaEvent_t> chunk_ev; // [thread * nchunks + chunk]
+  std::vector<uint8_t> has_ev;       // same indexing: thread t had pieces in chunk c
+  std::unique_ptr<std::atomic<int>[]> progress; // per thread: chunks fully issued
+  std::atomic<int> failed{0};
+  uint32_t nchunks = 0;
+  int dev = 0;
+
+  void add(const ChunkArray& a, const uint32_t* coff, const uint32_t* csize, uint32_t nch)
+  {
+    for (uint32_t c = 0; c < nch; c++) {
+      size_t off = (size_t)coff[c] * a.elem_bytes, left = (size_t)csize[c] * a.elem_bytes;
+      while (left) {
+        const size_t b = std::min(left, COPIER_SLOT_BYTES);
+        pieces.push_back({a.host + off, a.dev + off, b, c});
+        off += b;
+        left -= b;
+      }
+    }
+  }
+  void run_thread(int t, int T)
+  {
+    cudaSetDevice(dev);
+    CopierCtx* c = ctx[t];
+    int k = 0;
+    uint32_t cur_chunk = 0;
+    bool any_in_chunk = false;
+    auto close_chunks_until = [&](uint32_t upto) { // chunks [cur_chunk, upto) are complete for this thread
+      while (cur_chunk < upto) {
+        if (any_in_chunk) {
+          cudaEventRecord(chunk_ev[(size_t)t * nchunks + cur_chunk], c->st);
+          has_ev[(size_t)t * nchunks + cur_chunk] = 1;
+        }
+        any_in_chunk = false;
+        cur_chunk++;
+        progress[t].store((int)cur_chunk, std::memory_order_release);
+      }
+    };
+    for (size_t i = (size_t)t; i < pieces.size(); i += (size_t)T) {
+      const Piece& pc = pieces[i];
+      close_chunks_until(pc.chunk);
+      const int sl = k & 1;
+      if (k >= 2 && cudaEventSynchronize(c->slot_free[sl]) != cudaSuccess) failed.store(1);
+      memcpy(c->slot[sl], pc.src, pc.bytes);
+      if (cudaMemcpyAsync(pc.dst, c->slot[sl], pc.bytes, cudaMemcpyHostToDevice, c->st) != cudaSuccess) failed.store(1);
+      cudaEventRecord(c->slot_free[sl], c->st);
+      any_in_chunk = true;
+      k++;
+    }
+    close_chunks_until(nchunks);
+  }
+  int start(DeviceRes* res, uint32_t nch, cudaEvent_t ready)
+  {
+    nchunks = nch;
+    cudaGetDevice(&dev);
+    // the pieces must be ordered by chunk across both arrays so that chunk i completes early: stable sort by chunk
+    std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) { return x.chunk < y.chunk; });
+    int T = (int)std::min<size_t>(8, std::max<unsigned>(2, std::thread::hardware_concurrency() / 4));
+    T = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, pieces.size()));
+    for (int t = 0; t < T; t++) {
+      CopierCtx* c = res->copier((size_t)t);
+      if (!c) return B200_ALLOCATION_FAILED;
+      ctx.push_back(c);
+      cudaStreamWaitEvent(c->st, ready, 0); // the staging buffers exist and earlier work on the caller's stream is done
+    }
+    chunk_ev.resize((size_t)T * nch);
+    has_ev.assign((size_t)T * nch, 0);
+    for (size_t i = 0; i < chunk_ev.size(); i++) chunk_ev[i] = res->event(64 + i);
+    progress.reset(new std::atomic<int>[T]);
+    for (int t = 0; t < T; t++) progress[t].store(0);
+    for (int t = 0; t < T; t++) threads.emplace_back([this, t, T] { run_thread(t, T); });
+    return B200_SUCCESS;
+  }
+  // make stream s wait for chunk c's copies (blocks the HOST until every copier thread has issued them)
+  void wait_chunk(uint32_t c, cudaStream_t s)
+  {
+    const int T = (int)threads.size();
+    for (int t = 0; t < T; t++) {
+      while (progress[t].load(std::memory_order_acquire) <= (int)c) std::this_thread::yield();
+      if (has_ev[(size_t)t * nchunks + c]) cudaStreamWaitEvent(s, chunk_ev[(size_t)t * nchunks + c], 0);
+    }
+  }
+  void join()
+  {
+    for (auto& th : threads) th.join();
+    threads.clear();
+  }
+  ~PageableCopy() { join(); }
+};
+
 template <class C>
-int msm_pipelined(const void* scalars, const void* bases, uint32_t n, const b200_msm_config* cfg, void* results)
+int msm_chunked(const void* scalars, const void* bases, uint32_t n, const b200_msm_config* cfg, void* results, HostKind ks, HostKind kp)
 {
   typedef typename C::Scalar S;
   typedef typename C::Base F;
@@ -805,14 +977,29 @@ int msm_pipelined(const void* scalars, const void* bases, uint32_t n, const b200
   constexpr int AW = 2 * F::N, XW = 4 * F::N, PW = 3 * F::N;
   constexpr uint32_t MAX_CHUNKS = 32;
   cudaStream_t s = (cudaStream_t)cfg->stream;
-  cudaStream_t cs = copy_stream_for_current_device();
-  if (!cs) return B200_UNKNOWN_ERROR;
+  DeviceRes* res = device_res();
+  if (!res) return B200_UNKNOWN_ERROR;
+  cudaStream_t cs = res->copy_stream;
   b200_msm_config sub = *cfg;
   sub.batch_size = 1;
   const MsmPlan pl = make_plan<C>((int)n, &sub); // one window size for all chunks: they share the bucket array
   const uint32_t pf = (uint32_t)pl.pf;
+  const bool any_host = (ks != HK_DEVICE) || (kp != HK_DEVICE);
   uint32_t csize[MAX_CHUNKS], coff[MAX_CHUNKS];
-  const uint32_t nchunks = pipeline_schedule(n, csize, MAX_CHUNKS);
+  uint32_t nchunks;
+  if (any_host) {
+    nchunks = pipeline_schedule(n, csize, MAX_CHUNKS);
+  } else {
+    const uint32_t cap = device_chunk_points(pl);
+    nchunks = std::min<uint32_t>(MAX_CHUNKS, (n + cap - 1) / cap);
+    const uint32_t each = (n + nchunks - 1) / nchunks;
+    uint32_t left = n;
+    for (uint32_t i = 0; i < nchunks; i++) {
+      csize[i] = std::min(each, left);
+      left -= csize[i];
+    }
+    if (left) return B200_INVALID_ARGUMENT; // > 32 * 2^30 / windows points
+  }
   uint32_t max_chunk = 0;
   for (uint32_t i = 0, o = 0; i < nchunks; o += csize[i], i++) {
     coff[i] = o;
@@ -820,40 +1007,69 @@ int msm_pipelined(const void* scalars, const void* bases, uint32_t n, const b200
   }
   const uint64_t n_buckets = (uint64_t)pl.nbm << (pl.c - 1);
   int err;
-  Scratch d_s, d_p, d_bkt, d_tmp, s_res;
-  if ((err = d_s.alloc((size_t)n * S::BYTES, s))) return err;
-  if ((err = d_p.alloc((size_t)n * pf * AW * 4, s))) return err;
+  Scratch d_s, d_p, d_pm, d_bkt, d_tmp, s_res;
+  ChunkArray as, ap;
+  as.kind = ks; as.elem_bytes = S::BYTES; as.host = (const uint8_t*)scalars; as.dev = (uint8_t*)const_cast<void*>(scalars);
+  ap.kind = kp; ap.elem_bytes = (size_t)pf * AW * 4; ap.host = (const uint8_t*)bases; ap.dev = (uint8_t*)const_cast<void*>(bases);
+  if (ks != HK_DEVICE) {
+    if ((err = d_s.alloc((size_t)n * S::BYTES, s))) return err;
+    as.dev = d_s.as<uint8_t>();
+  } else if (misaligned16(scalars)) {
+    return B200_INVALID_POINTER;
+  }
+  if (kp != HK_DEVICE) {
+    if ((err = d_p.alloc((size_t)n * ap.elem_bytes, s))) return err;
+    ap.dev = d_p.as<uint8_t>();
+  } else {
+    if (misaligned16(bases)) return B200_INVALID_POINTER;
+    // the caller's device points stay untouched: each chunk is converted into this scratch
+    if (!cfg->are_points_montgomery_form && (err = d_pm.alloc((size_t)max_chunk * ap.elem_bytes, s))) return err;
+  }
   if ((err = d_bkt.alloc((size_t)n_buckets * XW * 4, s))) return err;
   if (nchunks > 1 && (err = d_tmp.alloc((size_t)n_buckets * XW * 4, s))) return err;
   void* d_res;
   if ((err = stage_out(d_res, results, (size_t)PW * 4, cfg->are_results_on_device, s, s_res))) return err;
-  cudaEvent_t ready, copied[MAX_CHUNKS];
-  cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
-  for (uint32_t i = 0; i < nchunks; i++) cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
-  cudaEventRecord(ready, s); // staging buffers exist (stream-ordered allocation) and earlier work on s is ordered before the copies
-  cudaStreamWaitEvent(cs, ready, 0);
-  for (uint32_t i = 0; i < nchunks; i++) {
-    const uint32_t off = coff[i], cn = csize[i];
-    cudaMemcpyAsync(d_s.as<uint8_t>() + (size_t)off * S::BYTES, (const uint8_t*)scalars + (size_t)off * S::BYTES, (size_t)cn * S::BYTES,
-                    cudaMemcpyHostToDevice, cs);
-    cudaMemcpyAsync(d_p.as<uint8_t>() + (size_t)off * pf * AW * 4, (const uint8_t*)bases + (size_t)off * pf * AW * 4, (size_t)cn * pf * AW * 4,
-                    cudaMemcpyHostToDevice, cs);
-    cudaEventRecord(copied[i], cs);
+
+  // ---- copies ------------------------------------------------------------------------------------------------------------
+  PageableCopy pageable;
+  cudaEvent_t ready = res->event(0);
+  const bool direct_copies = (ks == HK_PINNED) || (kp == HK_PINNED);
+  const bool ring_copies = (ks == HK_PAGEABLE) || (kp == HK_PAGEABLE);
+  if (any_host) {
+    cudaEventRecord(ready, s); // staging buffers exist (stream-ordered allocation) and earlier work on s is ordered before the copies
+    if (direct_copies) {
+      cudaStreamWaitEvent(cs, ready, 0);
+      for (uint32_t i = 0; i < nchunks; i++) {
+        const size_t off = coff[i], cn = csize[i];
+        if (ks == HK_PINNED) cudaMemcpyAsync(as.dev + off * as.elem_bytes, as.host + off * as.elem_bytes, cn * as.elem_bytes, cudaMemcpyHostToDevice, cs);
+        if (kp == HK_PINNED) cudaMemcpyAsync(ap.dev + off * ap.elem_bytes, ap.host + off * ap.elem_bytes, cn * ap.elem_bytes, cudaMemcpyHostToDevice, cs);
+        cudaEventRecord(res->event(1 + i), cs);
+      }
+    }
+    if (ring_copies) {
+      if (ks == HK_PAGEABLE) pageable.add(as, coff, csize, nchunks);
+      if (kp == HK_PAGEABLE) pageable.add(ap, coff, csize, nchunks);
+      if ((err = pageable.start(res, nchunks, ready))) return err;
+    }
   }
+
   StageTimer prof;
   prof.begin(s);
   int rc = B200_SUCCESS;
   for (uint32_t i = 0; i < nchunks && rc == B200_SUCCESS; i++) {
     const uint32_t off = coff[i], cn = csize[i];
-    cudaStreamWaitEvent(s, copied[i], 0);
-    uint32_t* cp = d_p.as<uint32_t>() + (size_t)off * pf * AW;
+    if (direct_copies) cudaStreamWaitEvent(s, res->event(1 + i), 0);
+    if (ring_copies) pageable.wait_chunk(i, s);
+    const uint32_t* cp = (const uint32_t*)(ap.dev + (size_t)off * ap.elem_bytes);
     if (!cfg->are_points_montgomery_form) {
+      uint32_t* dst = (kp != HK_DEVICE) ? const_cast<uint32_t*>(cp) : d_pm.as<uint32_t>(); // our own staging copy converts in place
       const uint64_t ncoord = (uint64_t)cn * pf * 2 * (F::N / B::N);
       unsigned g = (unsigned)std::min<uint64_t>((ncoord + 255) / 256, (uint64_t)num_sms() * 16);
-      k_to_mont<B><<<g, 256, 0, s>>>(cp, cp, ncoord); B200_LAUNCHED(1);
+      k_to_mont<B><<<g, 256, 0, s>>>(cp, dst, ncoord); B200_LAUNCHED(1);
+      cp = dst;
     }
     uint32_t* target = (i == 0) ? d_bkt.as<uint32_t>() : d_tmp.as<uint32_t>();
-    rc = msm_core<C>(d_s.as<uint8_t>() + (size_t)off * S::BYTES, cp, cn, pl, 1, true, &sub, nullptr, s, prof, target, MSM_ACC);
+    rc = msm_core<C>(as.dev + (size_t)off * S::BYTES, cp, cn, pl, 1, true, &sub, nullptr, s, prof, target, MSM_ACC);
     if (rc == B200_SUCCESS && i > 0) {
       k_bucket_merge<F><<<(unsigned)((n_buckets + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(d_bkt.as<uint32_t>(), d_tmp.as<uint32_t>(), n_buckets);
       B200_LAUNCHED(1);
@@ -863,14 +1079,16 @@ int msm_pipelined(const void* scalars, const void* bases, uint32_t n, const b200
   }
   if (rc == B200_SUCCESS) rc = msm_core<C>(nullptr, nullptr, max_chunk, pl, 1, true, &sub, d_res, s, prof, d_bkt.as<uint32_t>(), MSM_RED);
   prof.mark("final");
-  prof.finish("msm_pipelined");
+  prof.finish(any_host ? "msm_pipelined" : "msm_chunked");
+  pageable.join();
+  if (pageable.failed.load()) rc = B200_COPY_FAILED;
   if (rc == B200_SUCCESS) rc = finish_out(results, d_res, (size_t)PW * 4, cfg->are_results_on_device, cfg->is_async, s);
-  if (rc != B200_SUCCESS) {
-    cudaStreamSynchronize(cs);
-    cudaStreamSynchronize(s);
+  if (rc != B200_SUCCESS || any_host) {
+    // host sources: the staging areas (Scratch, freed on `s`) must outlive the copies of the private streams
+    if (direct_copies) cudaStreamSynchronize(cs);
+    for (CopierCtx* c : pageable.ctx) cudaStreamSynchronize(c->st);
+    if (rc != B200_SUCCESS) cudaStreamSynchronize(s);
   }
-  cudaEventDestroy(ready);
-  for (uint32_t i = 0; i < nchunks; i++) cudaEventDestroy(copied[i]);
   return rc;
 }
 
@@ -884,11 +1102,16 @@ int msm_impl(const void* scalars, const void* bases, int msm_size, const b200_ms
   cudaStream_t s = (cudaStream_t)cfg->stream;
   const int batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
   if (msm_size <= 0) return B200_INVALID_ARGUMENT;
-  if (batch == 1 && !cfg->are_scalars_on_device && !cfg->are_points_on_device && (uint32_t)msm_size >= pipeline_min_points() &&
-      (uint64_t)msm_size * (cfg->precompute_factor > 0 ? cfg->precompute_factor : 1) < (1ull << 31) && !getenv("B200_MSM_NO_PIPELINE"))
-    return msm_pipelined<C>(scalars, bases, (uint32_t)msm_size, cfg, results);
   const MsmPlan pl = make_plan<C>(msm_size, cfg);
   const uint32_t n = (uint32_t)msm_size;
+  if ((uint64_t)n * pl.pf >= (1ull << 31)) return B200_INVALID_ARGUMENT;
+  const HostKind ks = host_kind(scalars, cfg->are_scalars_on_device), kp = host_kind(bases, cfg->are_points_on_device);
+  if (batch == 1) {
+    const bool any_host = (ks != HK_DEVICE) || (kp != HK_DEVICE);
+    const bool pipeline = any_host && n >= pipeline_min_points() && tune(T_MSM_NO_PIPELINE) <= 0;
+    const bool too_big = !any_host && n > device_chunk_points(pl);
+    if (pipeline || too_big || (any_host && n > device_chunk_points(pl))) return msm_chunked<C>(scalars, bases, n, cfg, results, ks, kp);
+  }
   const bool shared = cfg->are_points_shared_in_batch || batch == 1;
   const uint64_t n_points = (uint64_t)n * pl.pf * (shared ? 1 : batch);
   int err;
@@ -897,13 +1120,13 @@ int msm_impl(const void* scalars, const void* bases, int msm_size, const b200_ms
   Scratch s_scal, s_pts, s_pts_m, s_res;
   const void *d_scal, *d_pts;
   void* d_res;
-  if ((err = stage_in(d_scal, scalars, (size_t)n * batch * S::BYTES, cfg->are_scalars_on_device, s, s_scal))) return err;
-  if ((err = stage_in(d_pts, bases, (size_t)n_points * AW * 4, cfg->are_points_on_device, s, s_pts))) return err;
+  if ((err = stage_in(d_scal, scalars, (size_t)n * batch * S::BYTES, ks == HK_DEVICE, s, s_scal))) return err;
+  if ((err = stage_in(d_pts, bases, (size_t)n_points * AW * 4, kp == HK_DEVICE, s, s_pts))) return err;
   if ((err = stage_out(d_res, results, (size_t)batch * PW * 4, cfg->are_results_on_device, s, s_res))) return err;
   const uint32_t* pts_m = (const uint32_t*)d_pts;
   if (!cfg->are_points_montgomery_form) {
     uint32_t* dst;
-    if (!cfg->are_points_on_device) {
+    if (d_pts != bases) {
       dst = s_pts.as<uint32_t>(); // our own staging copy: convert in place
     } else {
       if ((err = s_pts_m.alloc((size_t)n_points * AW * 4, s))) return err;

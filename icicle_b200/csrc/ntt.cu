@@ -552,12 +552,8 @@ int launch_tile_pass_geom(const uint32_t* src, uint32_t* dst, const PassParams& 
 // developer knob: B200_NTT_GEOM="<loge><logt>" selects an alternative tile geometry for the 8-limb fields (tuning experiments)
 inline int tile_geom_override()
 {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* ev = getenv("B200_NTT_GEOM");
-    cached = ev ? atoi(ev) : 0;
-  }
-  return cached;
+  const int v = tune(T_NTT_GEOM);
+  return v > 0 ? v : 0;
 }
 
 template <class F>
@@ -663,13 +659,17 @@ int init_domain_impl(Domain* d, const void* primitive_root, cudaStream_t s)
   if ((err = pw_d.alloc((size_t)MAX_LOG_DOMAIN * F::BYTES, s))) return err;
   uint32_t* aux = nullptr;
   B200_CUDA_TRY(cudaMalloc(&aux, (size_t)(MAX_LOG_DOMAIN + 1) * F::BYTES), B200_ALLOCATION_FAILED);
+  struct AuxGuard { // frees the table on every early return below; disarmed once the domain owns it
+    uint32_t*& p;
+    bool armed = true;
+    ~AuxGuard() { if (armed && p) cudaFree(p); }
+  } aux_guard{aux};
   B200_CUDA_TRY(cudaMemcpyAsync(root_d.p, primitive_root, F::BYTES, cudaMemcpyHostToDevice, s), B200_COPY_FAILED);
   k_domain_setup<F><<<1, 1, 0, s>>>(root_d.as<uint32_t>(), info_d.as<uint32_t>(), aux, pw_d.as<uint32_t>()); B200_LAUNCHED(1);
   uint32_t order = 0;
   B200_CUDA_TRY(cudaMemcpyAsync(&order, info_d.p, 4, cudaMemcpyDeviceToHost, s), B200_COPY_FAILED);
   B200_CUDA_TRY(cudaStreamSynchronize(s), B200_SYNCHRONIZATION_FAILED);
   if (order == 0xffffffffu || order > 31) {
-    cudaFree(aux);
     fprintf(stderr, "[icicle_b200] ntt_init_domain: primitive root is not a 2^k-th root of unity (k <= 31)\n");
     return B200_INVALID_ARGUMENT; // cpu_ntt_domain.h:91-94
   }
@@ -678,14 +678,20 @@ int init_domain_impl(Domain* d, const void* primitive_root, cudaStream_t s)
   cudaError_t ce = cudaMalloc(&tw, size * F::BYTES);
   if (ce != cudaSuccess) {
     (void)cudaGetLastError();
-    cudaFree(aux);
     return map_alloc_error(ce);
   }
+  struct TwGuard {
+    uint32_t* p;
+    bool armed = true;
+    ~TwGuard() { if (armed && p) cudaFree(p); }
+  } tw_guard{tw};
   constexpr int CHUNK = 64;
   uint64_t threads = (size + CHUNK - 1) / CHUNK;
   k_power_table<F, CHUNK><<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(pw_d.as<uint32_t>(), nullptr, tw, size); B200_LAUNCHED(1);
   B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
   B200_CUDA_TRY(cudaStreamSynchronize(s), B200_SYNCHRONIZATION_FAILED);
+  aux_guard.armed = false;
+  tw_guard.armed = false;
   d->twiddles = tw;
   d->aux = aux;
   d->max_log = (int)order;
@@ -786,8 +792,8 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
   if ((err = stage_out(dout, output, bytes, cfg->are_outputs_on_device, s, sout))) return err;
 
   if constexpr (F::N == 1) {
-    if (cfg->columns_batch && batch > 1 && n_log >= 10 && cfg->ext_ntt_algorithm != B200_NTT_ALG_RADIX2 && !getenv("B200_NTT31_OFF") &&
-        !getenv("B200_NTT_COLUMNS_STRIDED")) {
+    if (cfg->columns_batch && batch > 1 && n_log >= 10 && cfg->ext_ntt_algorithm != B200_NTT_ALG_RADIX2 && tune(T_NTT31_OFF) <= 0 &&
+        tune(T_NTT_COLUMNS_STRIDED) <= 0) {
       if ((err = ntt_columns_transposed<F>(d, din, dout, size, batch, dir, cfg, s))) return err;
       return finish_out(output, dout, bytes, cfg->are_outputs_on_device, cfg->is_async, s);
     }
@@ -832,18 +838,18 @@ int ntt_impl(Domain* d, const void* input, int size, int dir, const b200_ntt_con
   // Mixed-radix tile passes (v2) for row-major batches with at least one full tile and fields that fit the tile in shared
   // memory; register-only radix-2^k passes (v1) otherwise, and always when the caller asks for Radix2.
   int maxr = (cfg->ext_ntt_algorithm == B200_NTT_ALG_RADIX2) ? 1 : (F::N >= 12 ? 3 : 4);
-  if (const char* ev = getenv("B200_NTT_MAXR")) maxr = std::max(1, std::min(4, atoi(ev)));
+  if (tune(T_NTT_MAXR) > 0) maxr = std::max(1, std::min(4, tune(T_NTT_MAXR)));
   bool use_tiles = (cfg->ext_ntt_algorithm != B200_NTT_ALG_RADIX2) && !cfg->columns_batch && n_log >= 5 &&
                    total >= ((uint64_t)1 << tile_log_for<F>()) && F::N <= 12;
-  if (const char* ev = getenv("B200_NTT_TILES")) use_tiles = use_tiles && atoi(ev) != 0;
+  if (tune(T_NTT_TILES) >= 0) use_tiles = use_tiles && tune(T_NTT_TILES) != 0;
   int radices[32];
   int max_s = std::min(TileCfg<F>::MAX_S, tile_log_for<F>());
-  if (const char* ev = getenv("B200_NTT_MAXS")) max_s = std::max(5, std::min(atoi(ev), tile_log_for<F>()));
+  if (tune(T_NTT_MAXS) > 0) max_s = std::max(5, std::min(tune(T_NTT_MAXS), tile_log_for<F>()));
   // 4-byte fields, natural order in and out: dedicated 32-column tile pass (ntt31.cuh), 5..9 stages per pass
   bool fast31 = false;
   if constexpr (F::N == 1) {
     fast31 = (cfg->ext_ntt_algorithm != B200_NTT_ALG_RADIX2) && !cfg->columns_batch && !gather_in && n_log >= 10 &&
-             !getenv("B200_NTT31_OFF");
+             tune(T_NTT31_OFF) <= 0;
     if (fast31) {
       max_s = 9;
       use_tiles = true;
@@ -1091,6 +1097,21 @@ __attribute__((visibility("hidden"))) int b200_internal_ntt_domain(int field, co
   *tw = d->valid ? d->twiddles : nullptr;
   *aux = d->valid ? d->aux : nullptr;
   *max_log = d->valid ? d->max_log : 0;
+  return B200_SUCCESS;
+}
+
+// internal: the primitive root (standard form, as the caller passed it) of the current device's domain -- the multi-GPU
+// orchestrator replicates the domain on the other devices with it (multi_gpu.cu)
+__attribute__((visibility("hidden"))) int b200_internal_ntt_domain_root(int field, void* root_out, int* max_log)
+{
+  if (field < 0 || field >= B200_FIELD_COUNT) return B200_INVALID_ARGUMENT;
+  Domain* d;
+  int err = get_domain(field, &d);
+  if (err) return err;
+  std::lock_guard<std::mutex> lock(d->mu);
+  if (!d->valid) return B200_INVALID_ARGUMENT; // same as an NTT without a domain
+  memcpy(root_out, d->root, (size_t)b200_field_bytes(field));
+  *max_log = d->max_log;
   return B200_SUCCESS;
 }
 

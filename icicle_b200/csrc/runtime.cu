@@ -9,6 +9,8 @@ using namespace b200;
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <cctype>
+#include <cstdlib>
 namespace {
   std::atomic<long long> g_launches{0};
   std::atomic<int> g_profiling{0};
@@ -19,7 +21,65 @@ namespace {
   float g_prof_ms[StageTimer::MAX_STAGES];
 } // namespace
 
+namespace {
+  // ---- tuning knobs: B200_<NAME> read once at load; b200_set_tuning() afterwards ------------------------------------------
+  const char* const kTuneNames[b200::T_COUNT] = {
+    "msm_pair_levels", "msm_chunk_target", "msm_no_wide_loads", "msm_pipeline_min", "msm_pipeline_chunks", "msm_no_pipeline",
+    "msm_staging_mb", "msm_sort", "ntt_geom", "ntt31_off", "ntt_columns_strided", "ntt_maxr", "ntt_tiles", "ntt_maxs", "ntt31_two_pass"};
+  std::atomic<int> g_tune[b200::T_COUNT];
+  struct TuneInit {
+    TuneInit()
+    {
+      for (int i = 0; i < b200::T_COUNT; i++) {
+        std::string env = "B200_";
+        for (const char* c = kTuneNames[i]; *c; c++) env += (char)toupper((unsigned char)*c);
+        const char* v = getenv(env.c_str());
+        g_tune[i].store(v ? atoi(v) : -1);
+      }
+    }
+  } g_tune_init;
+
+  // ---- private scratch pools, one per device -----------------------------------------------------------------------------
+  std::mutex g_pool_mu;
+  cudaMemPool_t g_pools[64] = {};
+  bool g_pool_tried[64] = {};
+} // namespace
+
 namespace b200 {
+  int tune(Tune k) { return (k >= 0 && k < T_COUNT) ? g_tune[k].load(std::memory_order_relaxed) : -1; }
+
+  cudaMemPool_t scratch_pool()
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (g_pool_tried[dev]) return g_pools[dev]; // written once under the mutex below
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool_tried[dev]) return g_pools[dev];
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+      uint64_t thresh = UINT64_MAX; // keep freed scratch for the next call; b200_trim_scratch() / B200_SCRATCH_RETAIN_MB bound it
+      if (const char* ev = getenv("B200_SCRATCH_RETAIN_MB")) thresh = (uint64_t)atoll(ev) << 20;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+      g_pools[dev] = pool;
+    } else {
+      (void)cudaGetLastError();
+      g_pools[dev] = nullptr; // fall back to the device's default pool (cudaMallocAsync)
+    }
+    g_pool_tried[dev] = true;
+    return g_pools[dev];
+  }
+
+  StageTimer::~StageTimer()
+  {
+    if (!on) return; // finish() clears `on`; reaching here with it set means an early error return
+    for (int i = 0; i <= n; i++) cudaEventDestroy(ev[i]);
+  }
   void StageTimer::begin(cudaStream_t stream)
   {
     on = g_profiling.load() != 0;
@@ -50,6 +110,7 @@ namespace b200 {
       g_prof_names[i][31] = 0;
     }
     for (int i = 0; i <= n; i++) cudaEventDestroy(ev[i]);
+    on = false;
   }
 } // namespace b200
 
@@ -74,7 +135,35 @@ int b200_get_last_profile(char* names_out, int names_cap, float* ms_out, int max
   return k;
 }
 
-const char* b200_version(void) { return "icicle_b200 0.1 (sm_100a; MSM+NTT+vec-ops; C ABI v1)"; }
+int b200_set_tuning(const char* name, int value)
+{
+  if (!name) return B200_INVALID_POINTER;
+  for (int i = 0; i < b200::T_COUNT; i++) {
+    if (!strcmp(name, kTuneNames[i])) {
+      g_tune[i].store(value < 0 ? -1 : value);
+      return B200_SUCCESS;
+    }
+  }
+  return B200_INVALID_ARGUMENT;
+}
+int b200_get_tuning(const char* name)
+{
+  if (!name) return -1;
+  for (int i = 0; i < b200::T_COUNT; i++)
+    if (!strcmp(name, kTuneNames[i])) return g_tune[i].load();
+  return -1;
+}
+
+int b200_trim_scratch(size_t keep_bytes)
+{
+  cudaMemPool_t pool = b200::scratch_pool();
+  if (!pool) return B200_SUCCESS;
+  B200_CUDA_TRY(cudaDeviceSynchronize(), B200_SYNCHRONIZATION_FAILED);
+  B200_CUDA_TRY(cudaMemPoolTrimTo(pool, keep_bytes), B200_DEALLOCATION_FAILED);
+  return B200_SUCCESS;
+}
+
+const char* b200_version(void) { return "icicle_b200 0.2 (sm_100a; MSM+NTT+vec-ops; C ABI v2)"; }
 
 int b200_get_device_count(int* count)
 {
@@ -97,16 +186,6 @@ int b200_set_device(int device_id)
     return B200_INVALID_DEVICE;
   }
   B200_CUDA_TRY(cudaSetDevice(device_id), B200_INVALID_DEVICE);
-  // keep freed stream-ordered scratch in the pool: MSM/NTT temporaries are re-used call after call
-  static thread_local unsigned long long configured_mask = 0;
-  if (device_id < 64 && !(configured_mask & (1ull << device_id))) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
-      uint64_t thresh = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
-    }
-    configured_mask |= (1ull << device_id);
-  }
   return B200_SUCCESS;
 }
 

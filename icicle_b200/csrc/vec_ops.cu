@@ -137,8 +137,8 @@ int vec_op_impl(int op, const void* a, const void* b, uint64_t size, const b200_
   if ((err = stage_in(db, b, bytes, cfg->is_b_on_device, s, sb))) return err;
   void* user_out = (op == B200_VEC_ACCUMULATE) ? const_cast<void*>(a) : out;
   bool out_on_device = (op == B200_VEC_ACCUMULATE) ? (bool)cfg->is_a_on_device : (bool)cfg->is_result_on_device;
-  if (op == B200_VEC_ACCUMULATE && !out_on_device) {
-    dout = sa.p; // accumulate in the staged copy of a, then copy back
+  if (op == B200_VEC_ACCUMULATE) {
+    dout = const_cast<void*>(da); // in place: the caller's device buffer, or the staged copy of a (copied back by finish_out)
   } else if ((err = stage_out(dout, user_out, bytes, out_on_device, s, so))) {
     return err;
   }
@@ -490,7 +490,7 @@ int poly_divide_impl(const void* num, uint64_t num_size, const void* den, uint64
   const size_t qb = q_size * batch * F::BYTES, rb = r_size * batch * F::BYTES;
   if ((err = stage_out(dq, q, qb, cfg->is_result_on_device, s, sq))) return err;
   if ((err = stage_out(dr, r, rb, cfg->is_result_on_device, s, sr))) return err;
-  if (!cfg->is_result_on_device) B200_CUDA_TRY(cudaMemcpyAsync(dq, q, qb, cudaMemcpyHostToDevice, s), B200_COPY_FAILED); // keep untouched entries
+  if (dq != q) B200_CUDA_TRY(cudaMemcpyAsync(dq, q, qb, cudaMemcpyDefault, s), B200_COPY_FAILED); // keep untouched entries
   if ((err = sdeg.alloc((size_t)batch * 16, s))) return err;
   long long* ndeg = sdeg.as<long long>();
   long long* ddeg = ndeg + batch;
@@ -506,7 +506,7 @@ int poly_divide_impl(const void* num, uint64_t num_size, const void* den, uint64
   k_highest_nonzero<F><<<grid_for(den_size * batch), VEC_THREADS, 0, s>>>((const uint32_t*)dd, den_size, batch, cfg->columns_batch, ddeg); B200_LAUNCHED(1);
   k_poly_divide<F><<<batch, 256, 0, s>>>((const uint32_t*)dd, den_size, batch, cfg->columns_batch, ndeg, ddeg, (uint32_t*)dq, q_size, (uint32_t*)dr, r_size); B200_LAUNCHED(1);
   B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
-  if (!cfg->is_result_on_device) B200_CUDA_TRY(cudaMemcpyAsync(q, dq, qb, cudaMemcpyDeviceToHost, s), B200_COPY_FAILED);
+  if (dq != q) B200_CUDA_TRY(cudaMemcpyAsync(q, dq, qb, cudaMemcpyDefault, s), B200_COPY_FAILED);
   return finish_out(r, dr, rb, cfg->is_result_on_device, cfg->is_async, s);
 }
 

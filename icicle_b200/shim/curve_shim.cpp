@@ -58,6 +58,11 @@ namespace {
   eIcicleError msm_t(const Device&, const scalar_t* scalars, const A* bases, int msm_size, const MSMConfig& config, P* results)
   {
     b200_msm_config c = to_c(config);
+    // opt-in ConfigExtension key "multi_gpu" = number of devices: host-resident inputs/outputs are sharded over
+    // that many GPUs, one host thread each (the reference's own multi-device model, multi-device.md:32-36)
+    const int multi = ext_int(config.ext, "multi_gpu", 0);
+    if (multi > 1 && !c.are_scalars_on_device && !c.are_points_on_device && !c.are_results_on_device)
+      return to_err(b200_msm_multi_gpu(CURVE, scalars, bases, msm_size, &c, results, multi, nullptr));
     return to_err(b200_msm(CURVE, scalars, bases, msm_size, &c, results));
   }
   template <int CURVE, class A>

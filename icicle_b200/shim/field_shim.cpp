@@ -131,7 +131,11 @@ namespace {
   eIcicleError ntt_impl(const Device&, const scalar_t* in, int size, NTTDir dir, const NTTConfig<scalar_t>& config, scalar_t* out)
   {
     b200_ntt_config c = to_c(config);
-    return to_err(b200_ntt(FIELD, in, size, dir == NTTDir::kForward ? B200_NTT_FORWARD : B200_NTT_INVERSE, &c, out));
+    const int d = dir == NTTDir::kForward ? B200_NTT_FORWARD : B200_NTT_INVERSE;
+    // opt-in ConfigExtension key "multi_gpu" = number of devices: a host-resident row batch is sharded by batch index
+    const int multi = ext_int(config.ext, "multi_gpu", 0);
+    if (multi > 1 && !c.are_inputs_on_device && !c.are_outputs_on_device) return to_err(b200_ntt_multi_gpu(FIELD, in, size, d, &c, out, multi, nullptr));
+    return to_err(b200_ntt(FIELD, in, size, d, &c, out));
   }
   #ifdef EXT_FIELD
   // NttExtFieldImpl (ntt_backend.h:32-48): extension_t elements, scalar_t twiddles / coset generator / domain

@@ -252,6 +252,23 @@ B200_API int b200_projective_convert_montgomery(int curve, const void* in, uint6
  * ncclReduce cannot add group elements).  Uses the is_a_on_device / is_result_on_device / stream fields of cfg. */
 B200_API int b200_ec_sum(int curve, const void* points, int n, const b200_vec_ops_config* cfg, void* out);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU orchestration.  The reference API is one device per call and prescribes "one host thread per
+ * device" (docs/docs/start/architecture/multi-device.md:32-36,76; wrappers/rust/icicle-core/src/msm/tests.rs:26-40); these
+ * entry points do exactly that inside the backend: HOST-resident inputs/outputs, one host thread per device, the ordinary
+ * single-device path on each shard.  Batches shard by batch index (no exchange); one large MSM shards by point range and
+ * the per-device partial results are summed with b200_ec_sum (the only exchange: n_devices * |projective| bytes).
+ * device_ids == NULL means devices 0 .. n_devices-1; n_devices <= 0 means all visible devices.  The registration shims
+ * call them when the caller's ConfigExtension carries the opt-in key "multi_gpu" (number of devices).
+ * ---------------------------------------------------------------------------------------------------------------- */
+B200_API int b200_msm_multi_gpu(int curve, const void* scalars, const void* bases, int msm_size, const b200_msm_config* cfg, void* results,
+                                int n_devices, const int* device_ids);
+/* batched NTT: batch rows are partitioned; the twiddle domain of the CURRENT device is replicated on the others */
+B200_API int b200_ntt_multi_gpu(int field, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output,
+                                int n_devices, const int* device_ids);
+/* the contiguous split both deployments use (threads here, one process per GPU in bench.py): part `index` of `parts` */
+B200_API void b200_shard_range(uint64_t total, int parts, int index, uint64_t* begin, uint64_t* count);
+
 /* ---- instrumentation (not part of the reference API; used by bench.py and the profiling scripts) ---- */
 /* number of kernels of THIS library launched so far in the process (library kernels such as cub's are not counted) */
 B200_API long long b200_get_launch_count(void);
@@ -259,6 +276,17 @@ B200_API long long b200_get_launch_count(void);
 B200_API void b200_set_profiling(int on);
 /* stage timings of the last profiled call: names_out = "what,stage0,stage1,..."; returns the number of stages */
 B200_API int b200_get_last_profile(char* names_out, int names_cap, float* ms_out, int max_stages);
+
+/* developer / test knobs (msm_pair_levels, msm_pipeline_min, msm_pipeline_chunks, msm_no_pipeline, msm_chunk_target,
+ * msm_no_wide_loads, msm_staging_mb, msm_sort, ntt_geom, ntt31_off, ntt_columns_strided, ntt_maxr, ntt_tiles, ntt_maxs,
+ * ntt31_two_pass): initialised ONCE from the environment (B200_<NAME>) when the library loads -- the hot path never calls
+ * getenv() -- and changed afterwards only here; value < 0 = unset (built-in policy).  Returns INVALID_ARGUMENT for an unknown name. */
+B200_API int b200_set_tuning(const char* name, int value);
+B200_API int b200_get_tuning(const char* name);
+/* The library's temporaries come from a PRIVATE stream-ordered pool per device (the process-wide default pool and device
+ * limits are never modified); freed scratch is retained there between calls (bounded by B200_SCRATCH_RETAIN_MB at load).
+ * b200_trim_scratch() synchronises the current device and returns everything above keep_bytes to the driver. */
+B200_API int b200_trim_scratch(size_t keep_bytes);
 
 /* library version / build info string (static storage) */
 B200_API const char* b200_version(void);

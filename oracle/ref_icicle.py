@@ -111,6 +111,42 @@ class Ref:
         _chk(self.dev.icicle_get_registered_devices(buf, 256), "get_registered_devices")
         return buf.value.decode().split(",")
 
+    def config_extension(self, **ints):
+        """ConfigExtension* with integer keys (icicle/src/config_extension.cpp:7-15); pass it as `ext=` of a config.  Leaked on
+        purpose (tests only)."""
+        self.dev.create_config_extension.restype = C.c_void_p
+        self.dev.config_extension_set_int.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        ext = self.dev.create_config_extension()
+        for k, v in ints.items():
+            self.dev.config_extension_set_int(ext, k.encode(), int(v))
+        return ext
+
+    def malloc(self, nbytes):
+        """icicle_malloc on the active device (icicle/src/runtime.cpp)."""
+        ptr = C.c_void_p()
+        self.dev.icicle_malloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        _chk(self.dev.icicle_malloc(C.byref(ptr), nbytes), "icicle_malloc")
+        return ptr
+
+    def free(self, ptr):
+        self.dev.icicle_free.argtypes = [C.c_void_p]
+        _chk(self.dev.icicle_free(ptr), "icicle_free")
+
+    def copy_to_device(self, dptr, host):
+        self.dev.icicle_copy_to_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        _chk(self.dev.icicle_copy_to_device(dptr, host.ctypes.data, host.nbytes), "icicle_copy_to_device")
+
+    def copy_to_host(self, host, dptr):
+        self.dev.icicle_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        _chk(self.dev.icicle_copy_to_host(host.ctypes.data, dptr, host.nbytes), "icicle_copy_to_host")
+
+    def msm_precompute_bases_raw(self, bases_ptr, n, out_ptr, g2=False, **cfgkw):
+        """<curve>_msm_precompute_bases with caller-supplied raw pointers (device or host) and config flags as given."""
+        cfg = self.msm_config(**cfgkw)
+        fn = self._f(self.curve, ("g2_" if g2 else "") + "msm_precompute_bases")
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        _chk(fn(bases_ptr, C.c_int(n), C.byref(cfg), out_ptr), "msm_precompute_bases")
+
     # ---- helpers -------------------------------------------------------------------------------------------------------
     def _f(self, lib, sym):
         return getattr(lib, f"{self.name}_{sym}")

@@ -18,6 +18,39 @@ def rand_field_elems(field_name, n, seed, as_ints=False):
     return vals if as_ints else utils.to_limbs(vals, fp["limbs"])
 
 
+def seeded_scalars(field_name, n, seed):
+    """n uniform-looking field elements as (n, limbs) uint32, fast enough for 2^26+: random 32-bit limbs with the top limb
+    reduced below the modulus' top limb (so every value is < p).  Used identically by the GPU tests and tests/ref_worker.py."""
+    fp = utils.field_params(field_name)
+    L, p = fp["limbs"], fp["p"]
+    rs = np.random.default_rng(seed)
+    if L == 1:
+        return rs.integers(0, p, size=(n, 1), dtype=np.uint32)
+    out = rs.integers(0, 1 << 32, size=(n, L), dtype=np.uint32)
+    top = p >> (32 * (L - 1))
+    out[:, L - 1] %= np.uint32(top)
+    return out
+
+
+def tiled_g1_points(curve_name, n, distinct, seed):
+    """n affine points = `distinct` DISTINCT curve points (gen_g1_points) tiled; (n, 2*limbs) uint32."""
+    base = gen_g1_points(curve_name, min(n, distinct), seed)
+    reps = (n + base.shape[0] - 1) // base.shape[0]
+    return np.ascontiguousarray(np.tile(base, (reps, 1))[:n])
+
+
+def fq2_projective_to_affine_ints(proj_limbs, limbs, q, nr):
+    """(X, Y, Z) over Fq2 (each {c0, c1}) -> [x0, x1, y0, y1] python ints; None at infinity."""
+    X0, X1, Y0, Y1, Z0, Z1 = utils.from_limbs(np.asarray(proj_limbs, dtype=np.uint32).reshape(6, limbs))
+    if Z0 == 0 and Z1 == 0:
+        return None
+    den = pow((Z0 * Z0 - nr * Z1 * Z1) % q, -1, q)
+    zi = (Z0 * den % q, (-Z1) * den % q)
+    mul = lambda a, b: ((a[0] * b[0] + nr * a[1] * b[1]) % q, (a[0] * b[1] + a[1] * b[0]) % q)
+    x, y = mul((X0, X1), zi), mul((Y0, Y1), zi)
+    return [x[0], x[1], y[0], y[1]]
+
+
 # ---- G1 affine arithmetic over python ints ------------------------------------------------------------------------------
 def ec_add(A, B, q):
     if A is None: return B

@@ -28,3 +28,18 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def tuning():
+    """Set developer knobs of the native library (b200_set_tuning) for one test; restored afterwards."""
+    import icicle_b200 as ib
+    touched = {}
+
+    def _set(name, value):
+        touched.setdefault(name, ib.get_tuning(name))
+        ib.set_tuning(name, value)
+
+    yield _set
+    for name, old in touched.items():
+        ib.set_tuning(name, old)

@@ -26,8 +26,14 @@ def affine_of(curve_limbs, q, proj):
 
 
 @pytest.mark.parametrize("name,curve,g2curve,fq,L", [("bn254", ib.Curve.BN254_G1, ib.Curve.BN254_G2, "bn254_fq", 8),
-                                                     ("bls12_381", ib.Curve.BLS12_381_G1, ib.Curve.BLS12_381_G2, "bls12_381_fq", 12)])
+                                                     ("bls12_381", ib.Curve.BLS12_381_G1, ib.Curve.BLS12_381_G2, "bls12_381_fq", 12),
+                                                     ("bls12_377", ib.Curve.BLS12_377_G1, ib.Curve.BLS12_377_G2, "bls12_377_fq", 12),
+                                                     ("bw6_761", ib.Curve.BW6_761_G1, ib.Curve.BW6_761_G2, "bw6_761_fq", 24),
+                                                     ("grumpkin", ib.Curve.GRUMPKIN, None, "bn254_fr", 8)])
 def test_msm_golden(name, curve, g2curve, fq, L):
+    """Every curve of the north-star list against outputs of ITS OWN reference build (tools/make_golden.py): G1 MSM (auto and
+    forced c, bitsize, batch, Montgomery inputs), the curve Montgomery conversion, and the G2 MSM (Fq2 for bn254 / bls12-381 /
+    bls12-377, Fq for bw6-761; grumpkin has no G2) -- mirrors icicle/tests/test_curve_api.cpp:275-289."""
     g = gold(name)
     q = utils.field_params(fq)["p"]
     s, P = g["msm_scalars"], g["msm_points"]
@@ -46,22 +52,31 @@ def test_msm_golden(name, curve, g2curve, fq, L):
                  ib.MSMConfig(are_scalars_montgomery_form=True, are_points_montgomery_form=True))
     assert affine_of(L, q, got[0]) == exp
     assert np.array_equal(ib.affine_convert_montgomery(curve, P, n, True), g["points_montgomery"])
-    # G2: compare affine coordinates in Fq2 (x = X/Z, y = Y/Z with Fq2 inversion done on integers)
+    if g2curve is None:
+        return
     P2 = g["g2_points"]
-    got = ib.msm(g2curve, s[:24], P2, 24)[0]
-    nr = utils.curve_params(name)["nonresidue"]
-    X0, X1, Y0, Y1, Z0, Z1 = utils.from_limbs(got.reshape(6, L))
-    den = pow((Z0 * Z0 - nr * Z1 * Z1) % q, -1, q)
-    zi = (Z0 * den % q, (-Z1) * den % q)
-    mul = lambda a, b: ((a[0] * b[0] + nr * a[1] * b[1]) % q, (a[0] * b[1] + a[1] * b[0]) % q)
-    x, y = mul((X0, X1), zi), mul((Y0, Y1), zi)
-    ex = utils.from_limbs(g["g2_msm_result_affine"].reshape(4, L))
-    assert [x[0], x[1], y[0], y[1]] == ex
+    for c in (0, 5):
+        got = ib.msm(g2curve, s[:24], P2, 24, ib.MSMConfig(c=c))[0]
+        if utils.curve_params(name)["g2"] == "fq":  # bw6-761: G2 lives over the base field itself
+            assert affine_of(L, q, got) == common.affine_limbs_to_ints(g["g2_msm_result_affine"], L)[0]
+            continue
+        # G2 over Fq2: compare affine coordinates (x = X/Z, y = Y/Z with the Fq2 inversion done on integers)
+        nr = utils.curve_params(name)["nonresidue"]
+        X0, X1, Y0, Y1, Z0, Z1 = utils.from_limbs(got.reshape(6, L))
+        den = pow((Z0 * Z0 - nr * Z1 * Z1) % q, -1, q)
+        zi = (Z0 * den % q, (-Z1) * den % q)
+        mul = lambda a, b: ((a[0] * b[0] + nr * a[1] * b[1]) % q, (a[0] * b[1] + a[1] * b[0]) % q)
+        x, y = mul((X0, X1), zi), mul((Y0, Y1), zi)
+        ex = utils.from_limbs(g["g2_msm_result_affine"].reshape(4, L))
+        assert [x[0], x[1], y[0], y[1]] == ex
 
 
 @pytest.mark.parametrize("name,field,fname", [("bn254", ib.Field.BN254_FR, "bn254_fr"), ("bls12_381", ib.Field.BLS12_381_FR, "bls12_381_fr"),
-                                              ("babybear", ib.Field.BABYBEAR, "babybear")])
+                                              ("babybear", ib.Field.BABYBEAR, "babybear"), ("bls12_377", ib.Field.BLS12_377_FR, "bls12_377_fr"),
+                                              ("bw6_761", ib.Field.BLS12_377_FQ, "bls12_377_fq"), ("stark252", ib.Field.STARK252, "stark252")])
 def test_ntt_and_vec_golden(name, field, fname):
+    """NTT (all orderings, cosets, column batch, both directions) and vec-ops of every NTT field of the north-star list
+    against ITS OWN reference build's outputs; bw6_761's scalar field is the 12-limb bls12_377 base field."""
     g = gold(name)
     L = utils.field_params(fname)["limbs"]
     logn = 6
@@ -178,3 +193,13 @@ def test_m31_vec_ops_golden():
     assert int(ib.vector_product(F, nz, n)[0, 0]) == prod
     with pytest.raises(ib.IcicleError):
         ib.ntt_init_domain(F, np.array([p - 1], dtype=np.uint32))
+
+
+def test_grumpkin_scalar_vec_ops_golden():
+    """Grumpkin has no NTT upstream (features.cmake): its scalar field (= bn254 base field) vec-ops against the reference build."""
+    g = gold("grumpkin")
+    field, L = ib.Field.BN254_FQ, 8
+    a, b = g["vec_a"].reshape(-1, L), g["vec_b"].reshape(-1, L)
+    assert np.array_equal(ib.vector_add(field, a, b, 50), g["vec_add"].reshape(-1, L))
+    assert np.array_equal(ib.vector_sub(field, a, b, 50), g["vec_sub"].reshape(-1, L))
+    assert np.array_equal(ib.vector_mul(field, a, b, 50), g["vec_mul"].reshape(-1, L))

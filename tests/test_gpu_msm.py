@@ -225,31 +225,31 @@ def test_pipelined_host_path_matches_device_path():
     assert common.projective_to_affine_ints(host, 8, q) == common.projective_to_affine_ints(dev, 8, q)
 
 
-def test_pipelined_host_path_vs_reference_small(ref, monkeypatch):
+def test_pipelined_host_path_vs_reference_small(ref, tuning):
     """The host-pointer pipeline (chunked H2D on a copy stream, per-chunk accumulation into one shared bucket array with the
     window size of the whole MSM, k_bucket_merge, one bucket reduction) forced at small sizes: same group element as the
     reference CPU backend for ragged chunk splits, chunk counts 1..7, forced pair levels and the degenerate inputs."""
     C = ib.Curve.BN254_G1
-    monkeypatch.setenv("B200_MSM_PIPELINE_MIN", "2")
+    tuning("msm_pipeline_min", 2)
     for n, chunks in ((2, 2), (3, 2), (1000, 3), ((1 << 12) + 17, 7), (1 << 13, 1), ((1 << 14) - 1, 5)):
-        monkeypatch.setenv("B200_MSM_PIPELINE_CHUNKS", str(chunks))
+        tuning("msm_pipeline_chunks", chunks)
         s = ref.generate_scalars(n)
         P = ref.generate_affine_points(n)   # 100 distinct points repeated: doublings inside buckets, across chunks too
         exp = ref.msm(s, P, n)
         for lv, c in ((0, 0), (2, 7), (1, 12), (0, 15)):
-            monkeypatch.setenv("B200_MSM_PAIR_LEVELS", str(lv))
+            tuning("msm_pair_levels", lv)
             got = ib.msm(C, s, P, n, ib.MSMConfig(c=c))
             assert ref.projective_eq(got[0], exp[0]), (n, chunks, lv, c)
     # the default graded schedule (1/16, 1/16, 1/8, 1/4, 1/4, rest)
-    monkeypatch.delenv("B200_MSM_PIPELINE_CHUNKS")
-    monkeypatch.setenv("B200_MSM_PAIR_LEVELS", "2")
+    tuning("msm_pipeline_chunks", None)
+    tuning("msm_pair_levels", 2)
     for n in (5, 100, (1 << 13) + 11):
         s = ref.generate_scalars(n)
         P = ref.generate_affine_points(n)
         assert ref.projective_eq(ib.msm(C, s, P, n, ib.MSMConfig(c=9))[0], ref.msm(s, P, n)[0]), n
     # bitsize=1 (one huge bucket), zero bases, Montgomery-form scalars, P + (-P) in different chunks
-    monkeypatch.setenv("B200_MSM_PIPELINE_CHUNKS", "4")
-    monkeypatch.setenv("B200_MSM_PAIR_LEVELS", "1")
+    tuning("msm_pipeline_chunks", 4)
+    tuning("msm_pair_levels", 1)
     n = 1 << 12
     s = ref.generate_scalars(n)
     P = ref.generate_affine_points(n)
@@ -269,15 +269,9 @@ def test_pipelined_host_path_vs_reference_small(ref, monkeypatch):
 
 
 @pytest.fixture
-def pair_levels_env():
-    """B200_MSM_PAIR_LEVELS forces the number of batched-affine pair levels (msm_pairs.cuh) regardless of size."""
-    import os
-    old = os.environ.get("B200_MSM_PAIR_LEVELS")
-    yield lambda v: os.environ.__setitem__("B200_MSM_PAIR_LEVELS", str(v))
-    if old is None:
-        os.environ.pop("B200_MSM_PAIR_LEVELS", None)
-    else:
-        os.environ["B200_MSM_PAIR_LEVELS"] = old
+def pair_levels_env(tuning):
+    """msm_pair_levels forces the number of batched-affine pair levels (msm_pairs.cuh) regardless of size."""
+    return lambda v: tuning("msm_pair_levels", v)
 
 
 def test_bn254_pair_levels_vs_reference(ref, pair_levels_env):

@@ -179,12 +179,12 @@ def test_small_field_tile_pass(field, name, dom_log):
         ib.ntt(field, xd, n, d, cfg(), y_new)
         inplace = xd.clone()
         ib.ntt(field, inplace, n, d, cfg(), inplace)
-        os.environ["B200_NTT31_OFF"] = "1"
+        ib.set_tuning("ntt31_off", 1)
         try:
             y_old = ib.device_empty(n * batch)
             ib.ntt(field, xd, n, d, cfg(), y_old)
         finally:
-            del os.environ["B200_NTT31_OFF"]
+            ib.set_tuning("ntt31_off", None)
         assert torch.equal(y_new.view(-1), y_old.view(-1))
         assert torch.equal(inplace.view(torch.int32).view(-1), y_new.view(torch.int32).view(-1))
     # (c) round trip at the full domain size
@@ -222,11 +222,11 @@ def test_small_field_columns_batch_transposed_path(field, name):
                     rows = ib.ntt(field, xt, n, d, ib.NTTConfig(batch_size=cols, ordering=o, coset_gen=cg)).reshape(cols, n)
                     got = ib.ntt(field, x.reshape(-1, 1), n, d, ib.NTTConfig(batch_size=cols, columns_batch=True, ordering=o, coset_gen=cg))
                     assert np.array_equal(got.reshape(n, cols), rows.T), (name, logn, cols, d, o, cg is not None)
-        os.environ["B200_NTT_COLUMNS_STRIDED"] = "1"
+        ib.set_tuning("ntt_columns_strided", 1)
         try:
             old = ib.ntt(field, x.reshape(-1, 1), n, ib.NTTDir.kForward, ib.NTTConfig(batch_size=cols, columns_batch=True, coset_gen=g))
         finally:
-            del os.environ["B200_NTT_COLUMNS_STRIDED"]
+            ib.set_tuning("ntt_columns_strided", None)
         dx = ib.to_device(x.reshape(-1, 1))
         ib.ntt(field, dx, n, ib.NTTDir.kForward, ib.NTTConfig(batch_size=cols, columns_batch=True, coset_gen=g, are_outputs_on_device=True), dx)
         assert np.array_equal(ib.to_host(dx).reshape(-1, 1), old), (name, logn, cols)

@@ -77,13 +77,13 @@ sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "o
 import torch, torch.distributed as dist, numpy as np
 import common, port
 from icicle_b200 import utils
-from icicle_b200.sharding import shard_range
+from icicle_b200 import shard_range
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
 rank, world = dist.get_rank(), dist.get_world_size()
 n = 64
 pts = common.gen_g1_points("bn254", n, 9, as_ints=True)
 sc = common.rand_field_elems("bn254_fr", n, 10, as_ints=True)
-lo, hi = shard_range(n, rank, world)
+lo, hi = shard_range(n, world, rank)
 part = port.msm("bn254", sc[lo:hi], pts[lo:hi], c=6)       # this rank's partial result (CPU oracle stands in for the GPU)
 buf = torch.tensor(np.array(utils.to_limbs([part[0], part[1]], 8)).astype(np.int64).reshape(-1))
 gathered = [torch.zeros_like(buf) for _ in range(world)]
@@ -109,7 +109,7 @@ def test_point_sharded_msm_two_ranks_gloo(tmp_path):
     assert all(p.returncode == 0 for p in procs), outs
 
 
-def test_pipeline_schedule(monkeypatch):
+def test_pipeline_schedule(tuning):
     """Chunk schedule of the host-pointer MSM pipeline (msm_impl.cuh pipeline_schedule; pure host logic): covers every point
     exactly once, starts with a small chunk (exposed H2D time) and ends with quarters (long bucket runs), honours the
     equal-chunks override and the test override that allows tiny chunks."""
@@ -119,23 +119,23 @@ def test_pipeline_schedule(monkeypatch):
         buf = (C.c_uint32 * 32)()
         k = capi.lib.b200_msm_pipeline_schedule(n, buf, 32)
         return [buf[i] for i in range(k)]
-    monkeypatch.delenv("B200_MSM_PIPELINE_CHUNKS", raising=False)
-    monkeypatch.delenv("B200_MSM_PIPELINE_MIN", raising=False)
+    tuning("msm_pipeline_chunks", None)
+    tuning("msm_pipeline_min", None)
     assert sched(1 << 26) == [1 << 22, 1 << 22, 1 << 23, 1 << 24, 1 << 24, 1 << 24]
     for n in ((1 << 23), (1 << 23) + 12345, (1 << 25) - 1, (1 << 27) + 7, (1 << 30)):
         s = sched(n)
         assert sum(s) == n and 1 <= len(s) <= 6 and all(c >= 1 << 20 for c in s), (n, s)
         assert s[0] <= max(n >> 4, 1 << 20)
     assert sched(1 << 20) == [1 << 20]
-    monkeypatch.setenv("B200_MSM_PIPELINE_CHUNKS", "4")
+    tuning("msm_pipeline_chunks", 4)
     assert sched(1 << 26) == [1 << 24] * 4
     s = sched((1 << 24) + 3)
     assert sum(s) == (1 << 24) + 3 and len(s) == 4
-    monkeypatch.setenv("B200_MSM_PIPELINE_MIN", "2")
-    monkeypatch.setenv("B200_MSM_PIPELINE_CHUNKS", "7")
+    tuning("msm_pipeline_min", 2)
+    tuning("msm_pipeline_chunks", 7)
     s = sched(4113)
     assert sum(s) == 4113 and len(s) == 7
-    monkeypatch.delenv("B200_MSM_PIPELINE_CHUNKS")
+    tuning("msm_pipeline_chunks", None)
     for n in (1, 2, 5, 100, 8203):
         s = sched(n)
         assert sum(s) == n and all(c > 0 for c in s), (n, s)

@@ -26,7 +26,7 @@ def aff(arr, limbs):
     return pts[0]
 
 
-@pytest.mark.parametrize("name", ["bn254"])
+@pytest.mark.parametrize("name", ["bn254", "bls12_377", "bw6_761", "grumpkin"])
 def test_port_msm_vs_golden(name):
     g = _gold(name)
     cp = utils.curve_params(name)
@@ -46,7 +46,7 @@ def test_port_msm_vs_golden(name):
     assert utils.from_limbs(g["scalars_montgomery"]) == [s * (1 << (32 * sl)) % r for s in sc]
 
 
-@pytest.mark.parametrize("name,field", [("bn254", "bn254_fr")])
+@pytest.mark.parametrize("name,field", [("bn254", "bn254_fr"), ("bls12_377", "bls12_377_fr"), ("bw6_761", "bls12_377_fq"), ("stark252", "stark252")])
 def test_port_ntt_and_vec_vs_golden(name, field):
     g = _gold(name)
     fp = utils.field_params(field)

@@ -28,9 +28,9 @@ torch.cuda.empty_cache()
 h_res = np.zeros((1, 24), dtype=np.uint32)
 for ch in chunk_list:
     if ch > 0:
-        os.environ["B200_MSM_PIPELINE_CHUNKS"] = str(ch)      # k equal chunks
+        ib.set_tuning("msm_pipeline_chunks", ch)      # k equal chunks
     else:
-        os.environ.pop("B200_MSM_PIPELINE_CHUNKS", None)      # 0 = the default graded schedule
+        ib.set_tuning("msm_pipeline_chunks", None)      # 0 = the default graded schedule
     ib.msm(C_, h_s, h_p, n, ib.MSMConfig(), h_res)
     ts = []
     for _ in range(3):

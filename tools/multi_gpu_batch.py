@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch, torch.distributed as dist
 import icicle_b200 as ib
 from icicle_b200 import utils
-from icicle_b200.sharding import shard_batch
+from icicle_b200 import shard_range as shard_batch
 import common
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -39,7 +39,7 @@ g = torch.Generator(device=dev); g.manual_seed(11)                      # identi
 S = torch.randint(-2**31, 2**31, (batch * n, 8), dtype=torch.int64, device=dev, generator=g).to(torch.int32)
 S[:, 7] &= 0x3FFFFFFF
 S = S.contiguous()
-lo, hi = shard_batch(batch, rank, world)
+lo, hi = shard_batch(batch, world, rank)
 mine = ib.device_empty((hi - lo) * 36, dev).view(hi - lo, 36)
 run = lambda: ib.msm(C, S[lo * n:hi * n], P, n, ib.MSMConfig(batch_size=hi - lo, is_async=True), mine)
 run(); t_msm = timed(run)
@@ -64,7 +64,7 @@ n = 1 << logn
 ib.ntt_init_domain(F, utils.to_limbs([pow(fp["rou"], 1 << (fp["two_adicity"] - logn), fp["p"])], 1)[0])
 g.manual_seed(12)
 X = torch.randint(0, fp["p"], (batch * n,), dtype=torch.int64, device=dev, generator=g).to(torch.int32).contiguous()
-lo, hi = shard_batch(batch, rank, world)
+lo, hi = shard_batch(batch, world, rank)
 Y = ib.device_empty((hi - lo) * n, dev)
 run = lambda: ib.ntt(F, X[lo * n:hi * n], n, ib.NTTDir.kForward, ib.NTTConfig(batch_size=hi - lo, is_async=True), Y)
 run(); t_ntt = timed(run)

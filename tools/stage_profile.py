@@ -20,7 +20,7 @@ out = ib.device_empty(24).view(1, 24)
 ib.set_profiling(True)
 for c, lv in [(c, lv) for c in cs for lv in levels]:
     if lv is not None:
-        os.environ["B200_MSM_PAIR_LEVELS"] = lv
+        ib.set_tuning("msm_pair_levels", int(lv))
     for rep in range(2):
         ib.msm(ib.Curve.BN254_G1, s, P, n, ib.MSMConfig(c=c, is_async=True), out)
     what, st = ib.last_profile()

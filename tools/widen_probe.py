@@ -40,9 +40,9 @@ for logn, cols in ((20, 64), (16, 256)):
     x = torch.randint(0, p, (n * cols,), dtype=torch.int64, device="cuda").to(torch.int32)
     y = ib.device_empty(n * cols)
     ms_t = timeit(lambda: ib.ntt(F, x, n, 0, ib.NTTConfig(batch_size=cols, columns_batch=True, is_async=True), y))
-    os.environ["B200_NTT_COLUMNS_STRIDED"] = "1"
+    ib.set_tuning("ntt_columns_strided", 1)
     ms_s = timeit(lambda: ib.ntt(F, x, n, 0, ib.NTTConfig(batch_size=cols, columns_batch=True, is_async=True), y))
-    del os.environ["B200_NTT_COLUMNS_STRIDED"]
+    ib.set_tuning("ntt_columns_strided", None)
     ms_r = timeit(lambda: ib.ntt(F, x, n, 0, ib.NTTConfig(batch_size=cols, is_async=True), y))
     print(f"babybear columns_batch ntt 2^{logn} x {cols}: transposed {ms_t:8.3f} ms ({n*cols/ms_t*1e-6:6.2f} G elem/s) | strided {ms_s:8.3f} ms | row-major batch {ms_r:8.3f} ms", flush=True)
 ib.ntt_release_domain(F)
