@@ -57,7 +57,7 @@ namespace {
 
   // one unit of MSM work: `count` consecutive MSMs of the batch starting at `batch0`, restricted to points [p0, p0 + pn)
   struct MsmUnit {
-    int device;
+    int worker; // index of the host thread / device slot that runs it (device ids may repeat)
     int batch0, count;
     uint64_t p0, pn;
     int slot; // index into the partial-result array (batch == 1 style units), -1 = writes straight to results
@@ -115,7 +115,7 @@ int b200_msm_multi_gpu(int curve, const void* scalars, const void* bases, int ms
     for (int d = 0; d < G; d++) {
       uint64_t b0, bc;
       shard_range((uint64_t)batch, G, d, &b0, &bc);
-      if (bc) units.push_back({devs[d], (int)b0, (int)bc, 0, n, -1});
+      if (bc) units.push_back({d, (int)b0, (int)bc, 0, n, -1});
     }
   } else {
     partial.resize((size_t)batch * ranges * pbytes);
@@ -124,7 +124,7 @@ int b200_msm_multi_gpu(int curve, const void* scalars, const void* bases, int ms
       for (int r = 0; r < ranges; r++) {
         uint64_t p0, pn;
         shard_range(n, ranges, r, &p0, &pn);
-        if (pn) units.push_back({devs[d % G], b, 1, p0, pn, b * ranges + r});
+        if (pn) units.push_back({d % G, b, 1, p0, pn, b * ranges + r});
         else memset(partial.data() + ((size_t)b * ranges + r) * pbytes, 0, pbytes); // (0,0,0) is skipped by the combine (Z == 0)
         d++;
       }
@@ -146,7 +146,7 @@ int b200_msm_multi_gpu(int curve, const void* scalars, const void* bases, int ms
         return;
       }
       for (const MsmUnit& u : units) {
-        if (u.device != devs[d] || rc[d] != B200_SUCCESS) continue;
+        if (u.worker != d || rc[d] != B200_SUCCESS) continue;
         b200_msm_config c = base;
         c.stream = st;
         c.batch_size = u.count;

@@ -1,5 +1,6 @@
-# GPU-box scratch runner used during development (gpurun -- 'bash tools/gpu_call.sh'): edit per experiment.  Default = the round check.
+# GPU-box scratch runner used during development (gpurun -- 'bash tools/gpu_call.sh'): edit per experiment.
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -8 > gpurun_out/t_full.log; cat gpurun_out/t_full.log
+nvidia-smi -L > gpurun_out/gpus.txt; nproc >> gpurun_out/gpus.txt; free -g | head -2 >> gpurun_out/gpus.txt
+timeout 2400 python -m pytest tests/ -x -q -m gpu --durations=15 2>&1 | tail -40 > gpurun_out/t_full.log; cat gpurun_out/t_full.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
-timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 1500 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 6000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
