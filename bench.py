@@ -500,8 +500,9 @@ def run_ntt_secondary(torch, ib, common, args, dev, peak, scalars, ref, have_fro
         ref.ntt_init_domain(root)
         ms = t_host(lambda: ref.ntt(hx, nn, 0))
         variants["frontend_pageable"] = {"value": nn / (ms * 1e-3), "ms_per_step": ms}
-        ref.ntt_release_domain()
+        ref.ntt_release_domain()           # releases the CUDA device's (= our) domain: restore it for the rest of the run
         ref.set_device("CPU", 0)
+        ib.ntt_init_domain(F, root)
     head = "frontend_pageable" if "frontend_pageable" in variants else "cabi_pageable"
     ntt["e2e"] = {"value": variants[head]["value"], "unit": "elements/s", "h2d_bytes_per_step": 32 * nn, "d2h_bytes_per_step": 32 * nn,
                   "ms_per_step": variants[head]["ms_per_step"], "path": head, "variants": variants}

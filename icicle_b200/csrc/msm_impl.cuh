@@ -439,10 +439,21 @@ MsmPlan make_plan(int msm_size, const b200_msm_config* cfg)
 }
 
 // number of MSMs of a batch processed together (entry counts must fit 31 bits and memory stays bounded)
-inline int batch_chunk(uint32_t n, const MsmPlan& pl, int batch, bool shared, const b200_msm_config* cfg)
+inline int batch_chunk(uint32_t n, const MsmPlan& pl, int batch, bool shared, const b200_msm_config* cfg, size_t coord_bytes = 32)
 {
   const uint64_t ent_per_msm = (uint64_t)n * pl.nwin;
-  const uint64_t max_entries = 1ull << 30;
+  uint64_t max_entries = 1ull << 30;
+  if (batch > 1 && ent_per_msm * 2 <= max_entries) {
+    // the sorted (key, value) lists (16 B/entry) plus the planar level buffers of the pair tree (~2.25 coordinates' worth per
+    // entry) must fit comfortably: wide curves (48- / 96-byte coordinates) get smaller batch chunks instead of losing the levels
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const uint64_t per_entry = 16 + (uint64_t)(2.25 * (double)coord_bytes * 2);
+      max_entries = std::max<uint64_t>(ent_per_msm, std::min<uint64_t>(max_entries, (uint64_t)(0.45 * (double)free_b) / per_entry));
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
   int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)batch, max_entries / std::max<uint64_t>(ent_per_msm, 1)));
   if (cfg->ext_nof_chunks > 0) chunk = std::min(chunk, std::max(1, (batch + cfg->ext_nof_chunks - 1) / cfg->ext_nof_chunks)); // never above the 2^30-entry cap
   if (!shared) { // point indices must fit 31 bits
@@ -482,7 +493,7 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
   int err;
   // ---- batch chunking so that entry counts fit 31 bits and memory stays bounded ----------------------------------------
   const uint64_t ent_per_msm = (uint64_t)n * pl.nwin;
-  int chunk = batch_chunk(n, pl, batch, shared, cfg);
+  int chunk = batch_chunk(n, pl, batch, shared, cfg, (size_t)F::BYTES);
   if ((uint64_t)n * pl.pf >= (1ull << 31) || ent_per_msm >= (1ull << 32)) return B200_INVALID_ARGUMENT;
 
   const uint64_t max_ent = ent_per_msm * chunk;

@@ -76,7 +76,7 @@ __attribute__((visibility("hidden"))) int B200_CAT(b200_msm_plan_levels_entry_, 
   const MsmPlan pl = make_plan<ThisCurve>(msm_size, cfg);
   const int batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
   const bool shared = cfg->are_points_shared_in_batch || batch == 1;
-  const int chunk = batch_chunk((uint32_t)msm_size, pl, batch, shared, cfg);
+  const int chunk = batch_chunk((uint32_t)msm_size, pl, batch, shared, cfg, (size_t)ThisCurve::Base::BYTES);
   const uint64_t max_ent = (uint64_t)msm_size * pl.nwin * chunk;
   const uint64_t max_buckets = ((uint64_t)pl.nbm * chunk) << (pl.c - 1);
   return choose_pair_levels(max_ent, max_buckets);

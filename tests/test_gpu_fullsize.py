@@ -183,7 +183,8 @@ def test_babybear_ntt_vs_reference_full_size(logn, batch):
     F = ib.Field.BABYBEAR
     n = 1 << logn
     d = _scratch_dir()
-    for direction, ordering in ((0, 0), (1, 1)):
+    # the reference needs ~2 min of CPU per 2^27 transform: forward kNN only at the maximum size, both directions at 2^24
+    for direction, ordering in (((0, 0),) if logn >= 27 else ((0, 0), (1, 1))):
         pre = os.path.join(d, f"bb_{logn}_{direction}")
         _worker("ntt", "babybear", logn, batch, direction, ordering, 900 + logn, pre)
         root, exp = np.load(pre + "_root.npy"), np.load(pre + "_expected.npy")
