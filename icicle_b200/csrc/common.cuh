@@ -70,6 +70,10 @@ struct Scratch {
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+} // namespace b200
+#include "hostcopy.cuh"
+namespace b200 {
+
 // The reference's are_*_on_device flags are hints that wrappers do not always set (the Rust precompute_bases passes a
 // DeviceSlice with the flag left false): trust a `true` flag, otherwise ask the driver what the pointer is.
 static inline bool ptr_on_device(const void* p, bool flag)
@@ -96,8 +100,9 @@ static inline int stage_in(const void*& dev_ptr, const void* src, size_t bytes, 
   }
   int err = buf.alloc(bytes, s);
   if (err) return err;
-  B200_CUDA_TRY(cudaMemcpyAsync(buf.p, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), B200_COPY_FAILED);
   dev_ptr = buf.p;
+  if (!on_device && bytes >= RING_MIN_BYTES && host_kind(src, false) == HK_PAGEABLE) return ring_h2d(buf.p, src, bytes, s);
+  B200_CUDA_TRY(cudaMemcpyAsync(buf.p, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), B200_COPY_FAILED);
   return B200_SUCCESS;
 }
 // Output staging: a device pointer to write results into (the user's if on device and aligned, scratch otherwise).
@@ -118,6 +123,7 @@ static inline int stage_out(void*& dev_ptr, void* dst, size_t bytes, bool on_dev
 static inline int finish_out(void* dst, const void* dev_ptr, size_t bytes, bool on_device, bool is_async, cudaStream_t s)
 {
   on_device = ptr_on_device(dst, on_device);
+  if (dst != dev_ptr && !on_device && bytes >= RING_MIN_BYTES && host_kind(dst, false) == HK_PAGEABLE) return ring_d2h(dst, dev_ptr, bytes, s); // blocks
   if (dst != dev_ptr)
     B200_CUDA_TRY(cudaMemcpyAsync(dst, dev_ptr, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s), B200_COPY_FAILED);
   if (!on_device || !is_async) B200_CUDA_TRY(cudaStreamSynchronize(s), B200_SYNCHRONIZATION_FAILED);

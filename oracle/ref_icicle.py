@@ -262,10 +262,11 @@ class Ref:
         _chk(self._f(self.field, "get_root_of_unity_from_domain")(C.c_uint64(logn), self._p(out)), "get_root_of_unity_from_domain")
         return out
 
-    def ntt(self, inp, size, direction, coset_gen=None, **cfgkw):
+    def ntt(self, inp, size, direction, coset_gen=None, out=None, **cfgkw):
         cfg = self.ntt_config(coset_gen, **cfgkw)
         inp = np.ascontiguousarray(inp, dtype=np.uint32)
-        out = np.zeros_like(inp)
+        if out is None:
+            out = np.zeros_like(inp)
         _chk(self._f(self.field, "ntt")(self._p(inp), C.c_int(size), C.c_int(direction), C.byref(cfg), self._p(out)), "ntt")
         return out
 
