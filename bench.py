@@ -613,6 +613,58 @@ def run_configs(torch, dist, ib, common, args, rank, world, dev, peak, scalars, 
     except Exception as e:  # noqa
         out.append({"config": "BabyBear NTT 2^27 x batch 128", "error": repr(e)})
 
+    # ---- ONE BN254 NTT spanning the GPUs: phase 1 -> NCCL all-to-all over NVLink -> phase 2 (csrc/ntt.cu b200_ntt_dist_phase1/2) ----
+    if world > 1 and (world & (world - 1)) == 0:
+        try:
+            F = ib.Field.BN254_FR
+            fp = utils.field_params("bn254_fr")
+            n_log = 26
+            a_log = (n_log + 1) // 2
+            b_log = n_log - a_log
+            A, B = 1 << a_log, 1 << b_log
+            ib.ntt_release_domain(F)
+            ib.ntt_init_domain(F, utils.to_limbs([pow(fp["rou"], 1 << (fp["two_adicity"] - n_log), fp["p"])], 8)[0])
+            slab0 = rand_scalars_dev(torch, (A * B) // world, 900 + rank, dev)          # this rank's column slab [A][B/world]
+            slab = slab0.clone()
+            recv = torch.empty_like(slab)
+            outb = torch.empty_like(slab)
+            a2a_ms = []
+
+            def one(direction=0, al=a_log, bl=b_log, src=None):
+                buf = slab if src is None else src
+                ib.capi.check(ib.capi.lib.b200_ntt_dist_phase1(int(F), buf.data_ptr(), al, bl, world, rank, direction, None), "dist_phase1")
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                dist.all_to_all_single(recv.view(-1), buf.view(-1))
+                e1.record()
+                ib.capi.check(ib.capi.lib.b200_ntt_dist_phase2(int(F), recv.data_ptr(), outb.data_ptr(), al, bl, world, rank, direction, None), "dist_phase2")
+                a2a_ms.append((e0, e1))
+
+            def fwd():
+                slab.copy_(slab0)
+                one()
+            ms = timed(torch, dist, world, dev, fwd, 3, warmup=2)
+            ex = [a.elapsed_time(b) for a, b in a2a_ms[-3:]]
+            a2a = sum(ex) / len(ex)
+            # parity: the inverse transform (dimensions swapped) of the result must give the input back, bit for bit
+            res = outb.clone()
+            one(1, b_log, a_log, res)
+            torch.cuda.synchronize()
+            ok = bool(torch.equal(outb.view(-1), slab0.view(-1)))
+            sent = (A * B // world) * 32 * (world - 1) / world                              # bytes this rank puts on NVLink per transform
+            out.append({"config": f"ONE BN254 NTT of 2^{n_log} spanning {world} GPUs (column slabs; 4-step with a single NCCL all_to_all_single over NVLink)",
+                        "n_gpus": world, "value": (A * B) / (ms * 1e-3), "unit": "elements/s", "ms_per_pass": ms, "scaling": "strong",
+                        "all_to_all_ms": a2a, "nvlink_gbs_per_gpu_each_way": sent / (a2a * 1e-3) / 1e9,
+                        "roofline": {"bound": "hbm", "achieved": 64.0 * (A * B // world) / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": 64.0 * (A * B // world) / (ms * 1e-3) / 1e9 / peak},
+                        "parity": {"what": "distributed inverse(distributed forward(x)) == x bit-exactly; distributed == single-device transform in tests/test_gpu_multi.py", "ok": alltrue(ok)}})
+            del slab, slab0, recv, outb, res
+            ib.ntt_release_domain(F)
+            torch.cuda.empty_cache()
+            ib.trim_scratch(0)
+        except Exception as e:  # noqa
+            out.append({"config": "ONE BN254 NTT spanning the GPUs", "error": repr(e)})
+
     # ---- strong scaling of ONE 2^26 BN254 MSM: the point range is partitioned, partials combined by all-gather + ec_sum ----------
     if world > 1:
         try:

@@ -107,6 +107,8 @@ SYMBOLS = {
     "b200_get_last_profile": (_i, [C.c_char_p, _i, C.POINTER(C.c_float), _i]),
     "b200_msm_multi_gpu": (_i, [_i, _vp, _vp, _i, C.POINTER(MsmConfigC), _vp, _i, C.POINTER(_i)]),
     "b200_ntt_multi_gpu": (_i, [_i, _vp, _i, _i, C.POINTER(NttConfigC), _vp, _i, C.POINTER(_i)]),
+    "b200_ntt_dist_phase1": (_i, [_i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200_ntt_dist_phase2": (_i, [_i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200_shard_range": (None, [_u64, _i, _i, C.POINTER(_u64), C.POINTER(_u64)]),
     "b200_set_tuning": (_i, [C.c_char_p, _i]),
     "b200_get_tuning": (_i, [C.c_char_p]),

@@ -20,6 +20,15 @@
 
 namespace b200 {
 
+int tune_copier_threads(); // common.cuh: tune(T_COPIER_THREADS)
+// host threads moving pageable memory through the pinned ring: enough to keep PCIe (~55 GB/s) busy with ~6-8 GB/s memcpys each
+inline int copier_thread_count()
+{
+  const int forced = tune_copier_threads();
+  if (forced > 0) return std::min(forced, 32);
+  return (int)std::min<size_t>(12, std::max<unsigned>(2, std::thread::hardware_concurrency() / 8));
+}
+
 struct CopierCtx {
   cudaStream_t st = nullptr;
   void* slot[2] = {nullptr, nullptr};
@@ -155,7 +164,7 @@ struct PageableCopy {
     cudaGetDevice(&dev);
     // the pieces must be ordered by chunk across both arrays so that chunk i completes early: stable sort by chunk
     std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& x, const Piece& y) { return x.chunk < y.chunk; });
-    int T = (int)std::min<size_t>(8, std::max<unsigned>(2, std::thread::hardware_concurrency() / 4));
+    int T = copier_thread_count();
     T = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, pieces.size()));
     for (int t = 0; t < T; t++) {
       CopierCtx* c = res->copier((size_t)t);
@@ -193,7 +202,7 @@ constexpr size_t RING_MIN_BYTES = 32u << 20;
 
 inline int ring_threads(size_t bytes)
 {
-  int T = (int)std::min<size_t>(8, std::max<unsigned>(2, std::thread::hardware_concurrency() / 4));
+  int T = copier_thread_count();
   return (int)std::max<size_t>(1, std::min<size_t>((size_t)T, bytes / COPIER_SLOT_BYTES));
 }
 

@@ -15,6 +15,8 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -62,6 +64,116 @@ namespace {
     uint64_t p0, pn;
     int slot; // index into the partial-result array (batch == 1 style units), -1 = writes straight to results
   };
+
+  // reusable barrier for the device threads of one call (C++17: no std::barrier)
+  class Barrier
+  {
+    std::mutex mu;
+    std::condition_variable cv;
+    int count, waiting = 0, generation = 0;
+
+  public:
+    explicit Barrier(int n) : count(n) {}
+    void wait()
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      const int gen = generation;
+      if (++waiting == count) {
+        waiting = 0;
+        generation++;
+        cv.notify_all();
+      } else {
+        cv.wait(lk, [&] { return gen != generation; });
+      }
+    }
+  };
+
+  bool coset_is_one(const void* g, size_t bytes)
+  {
+    if (!g) return true;
+    const uint32_t* w = (const uint32_t*)g;
+    if (w[0] != 1) return false;
+    for (size_t i = 1; i < bytes / 4; i++)
+      if (w[i]) return false;
+    return true;
+  }
+
+  // ONE host-resident transform of 2^n_log points over G devices: scatter column slabs, phase 1, all-to-all by peer copies over
+  // NVLink, phase 2, gather (see b200_ntt_dist_phase1/2 in ntt.cu).  Natural order in, natural order out.
+  int ntt_distributed(int field, const void* input, int n_log, int dir, void* output, const std::vector<int>& devs, const uint32_t* root)
+  {
+    const int G = (int)devs.size();
+    const int a_log = (n_log + 1) / 2, b_log = n_log - a_log;
+    const size_t E = (size_t)b200_field_bytes(field);
+    const size_t A = (size_t)1 << a_log, B = (size_t)1 << b_log;
+    const size_t slab_elems = (A * B) / (size_t)G, blk = slab_elems / (size_t)G; // block = (A/G) x (B/G) elements
+    std::vector<int> rc(G, B200_SUCCESS);
+    std::vector<uint8_t*> recv(G, nullptr);
+    Barrier bar(G);
+    std::vector<std::thread> threads;
+    for (int d = 0; d < G; d++) {
+      threads.emplace_back([&, d] {
+        auto fail = [&](int code) { if (rc[d] == B200_SUCCESS) rc[d] = code; };
+        cudaStream_t st = nullptr;
+        uint8_t *slab = nullptr, *out = nullptr;
+        if (cudaSetDevice(devs[d]) != cudaSuccess) fail(B200_INVALID_DEVICE);
+        if (rc[d] == B200_SUCCESS && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) fail(B200_STREAM_CREATION_FAILED);
+        if (rc[d] == B200_SUCCESS) {
+          for (int o = 0; o < G; o++) // NVLink peer access (already-enabled is fine; same device is skipped)
+            if (devs[o] != devs[d]) {
+              int can = 0;
+              cudaDeviceCanAccessPeer(&can, devs[d], devs[o]);
+              if (can && cudaDeviceEnablePeerAccess(devs[o], 0) != cudaSuccess) (void)cudaGetLastError();
+            }
+          if (b200_ntt_init_domain(field, root, st) != B200_SUCCESS) fail(B200_INVALID_ARGUMENT);
+          if (cudaMalloc(&slab, slab_elems * E) != cudaSuccess || cudaMalloc(&recv[d], slab_elems * E) != cudaSuccess || cudaMalloc(&out, slab_elems * E) != cudaSuccess) {
+            (void)cudaGetLastError();
+            fail(B200_OUT_OF_MEMORY);
+          }
+        }
+        // scatter: column slab d of the A x B view of the host array
+        if (rc[d] == B200_SUCCESS &&
+            cudaMemcpy2DAsync(slab, (B / G) * E, (const uint8_t*)input + (size_t)d * (B / G) * E, B * E, (B / G) * E, A, cudaMemcpyHostToDevice, st) != cudaSuccess)
+          fail(B200_COPY_FAILED);
+        if (rc[d] == B200_SUCCESS) {
+          const int e = b200_ntt_dist_phase1(field, slab, a_log, b_log, G, d, dir, st);
+          if (e) fail(e);
+        }
+        bar.wait(); // every recv buffer exists
+        bool all_ok = true;
+        for (int o = 0; o < G; o++) all_ok = all_ok && rc[o] == B200_SUCCESS;
+        if (all_ok) {
+          for (int o = 0; o < G; o++) { // my block o -> rank o's receive slot d
+            if (cudaMemcpyPeerAsync(recv[o] + (size_t)d * blk * E, devs[o], slab + (size_t)o * blk * E, devs[d], blk * E, st) != cudaSuccess) fail(B200_COPY_FAILED);
+          }
+          if (cudaStreamSynchronize(st) != cudaSuccess) fail(B200_SYNCHRONIZATION_FAILED);
+        }
+        bar.wait(); // every block has landed
+        all_ok = true;
+        for (int o = 0; o < G; o++) all_ok = all_ok && rc[o] == B200_SUCCESS;
+        if (all_ok) {
+          int e = b200_ntt_dist_phase2(field, recv[d], out, a_log, b_log, G, d, dir, st);
+          if (e) fail(e);
+          // gather: column slab d of the B x A view of the natural-order result
+          if (rc[d] == B200_SUCCESS &&
+              cudaMemcpy2DAsync((uint8_t*)output + (size_t)d * (A / G) * E, A * E, out, (A / G) * E, (A / G) * E, B, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            fail(B200_COPY_FAILED);
+        }
+        if (st) {
+          if (cudaStreamSynchronize(st) != cudaSuccess) fail(B200_SYNCHRONIZATION_FAILED);
+          cudaStreamDestroy(st);
+        }
+        bar.wait(); // nobody frees a buffer a peer may still read
+        cudaFree(slab);
+        cudaFree(recv[d]);
+        cudaFree(out);
+      });
+    }
+    for (auto& t : threads) t.join();
+    for (int d = 0; d < G; d++)
+      if (rc[d] != B200_SUCCESS) return rc[d];
+    return B200_SUCCESS;
+  }
 
 } // namespace
 
@@ -185,6 +297,24 @@ int b200_ntt_multi_gpu(int field, const void* input, int size, int dir, const b2
   int err = resolve_devices(n_devices, device_ids, devs);
   if (err) return err;
   const int batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
+  // ---- ONE large transform: span the devices (4-step with a single all-to-all over NVLink) -------------------------------------
+  {
+    int n_log = 0;
+    while ((1 << n_log) < size) n_log++;
+    int Gd = 1;
+    while (Gd * 2 <= (int)devs.size()) Gd *= 2; // a power of two of devices
+    const size_t ebytes0 = (size_t)b200_field_bytes(field);
+    if (batch == 1 && Gd > 1 && size > 0 && (size & (size - 1)) == 0 && n_log >= 16 && (n_log / 2) >= 8 && !cfg->columns_batch && cfg->ordering == B200_NN &&
+        coset_is_one(cfg->coset_gen, ebytes0) && (1 << (n_log / 2)) >= Gd) {
+      uint32_t root0[32];
+      int max_log0 = 0;
+      if ((err = b200_internal_ntt_domain_root(field, root0, &max_log0))) return err;
+      if (n_log > max_log0) return B200_INVALID_ARGUMENT;
+      devs.resize(Gd);
+      DeviceGuard guard;
+      return ntt_distributed(field, input, n_log, dir, output, devs, root0);
+    }
+  }
   int G = std::min<int>((int)devs.size(), batch);
   // a column batch shards by column groups, i.e. strided slices of the host matrix: handled on one device (the transposes
   // dominate); a single transform spanning devices is b200_ntt_distributed_* (4-step)

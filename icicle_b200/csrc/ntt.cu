@@ -1023,6 +1023,97 @@ int ntt_ext4_impl(Domain* d, const void* input, int size, int dir, const b200_nt
 
 } // namespace
 
+// ---- distributed (multi-GPU) single NTT: the two local phases around the one all-to-all -------------------------------------
+// A transform of N = A*B points held as COLUMN SLABS of the A x B row-major view of the natural-order array (rank r of G owns
+// columns [r*B/G, (r+1)*B/G), stored [A][B/G]):
+//   phase 1 (local)   A-point NTTs down the local columns, then the "four-step" factor w_N^(+-col*k) on element (k, col);
+//                     the slab is then G contiguous blocks of A/G rows: block s goes to rank s
+//   exchange          all-to-all of (A/G) x (B/G) blocks: NCCL (one process per GPU, bench.py) or peer copies over NVLink
+//                     (one host thread per GPU, multi_gpu.cu) -- the only place on this path where link bandwidth matters
+//   phase 2 (local)   rank s now holds rows k in its range with all B columns: B-point NTTs along the rows give
+//                     X[kb*A + k]; a local transpose leaves the column slab [B][A/G] of the B x A view of the natural output.
+// i.e. natural column-slabs in, natural column-slabs out (dimensions swapped), for both directions (the inverse runs the same
+// steps with w^-1 and the 1/A, 1/B scalings of the local inverse NTTs).  The reference stops at one device
+// (docs/docs/start/architecture/multi-device.md:28-36); mathematically this is the same DFT as ntt_cpu.h:69-232.
+template <class F, int CH>
+__global__ void __launch_bounds__(256) k_dist_twiddle(uint32_t* __restrict__ data, uint32_t a_rows, uint32_t cols, uint64_t col0, uint32_t n_log,
+                                                      uint32_t dom_log, const uint32_t* __restrict__ tw, int inverse)
+{
+  const uint64_t chunks_per_row = (cols + CH - 1) / CH;
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= chunks_per_row * a_rows) return;
+  const uint64_t k = g / chunks_per_row, c0 = (g % chunks_per_row) * CH;
+  if (k == 0) return; // w^0
+  const uint64_t nmask = (1ull << n_log) - 1;
+  const uint32_t sh = dom_log - n_log;
+  uint64_t e0 = (k * (col0 + c0)) & nmask, ek = k;
+  if (inverse) {
+    e0 = (0 - e0) & nmask;
+    ek = (0 - ek) & nmask;
+  }
+  F t = load_twiddle<F>(tw, e0 << sh);
+  const F ratio = load_twiddle<F>(tw, ek << sh);
+  uint32_t* row = data + (k * cols + c0) * F::N;
+#pragma unroll
+  for (int j = 0; j < CH; j++) {
+    if (c0 + j < cols) {
+      store_fp<F>(row + (size_t)j * F::N, load_fp<F>(row + (size_t)j * F::N) * t);
+      t = t * ratio;
+    }
+  }
+}
+
+template <class F>
+int ntt_dist_phase1_impl(Domain* d, void* data, int a_log, int b_log, int n_ranks, int rank, int dir, cudaStream_t s)
+{
+  if (!d->valid) return B200_INVALID_ARGUMENT;
+  const int n_log = a_log + b_log;
+  if (n_log > d->max_log) return B200_INVALID_ARGUMENT;
+  const uint32_t A = 1u << a_log, cols = (1u << b_log) / (uint32_t)n_ranks;
+  b200_ntt_config c;
+  memset(&c, 0, sizeof(c));
+  c.stream = s;
+  c.batch_size = (int)cols;
+  c.columns_batch = 1;
+  c.are_inputs_on_device = c.are_outputs_on_device = c.is_async = 1;
+  c.ordering = B200_NN;
+  int err = ntt_impl<F>(d, data, (int)A, dir, &c, data);
+  if (err) return err;
+  constexpr int CH = (F::N == 1) ? 8 : 4;
+  const uint64_t threads = (uint64_t)A * ((cols + CH - 1) / CH);
+  k_dist_twiddle<F, CH><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>((uint32_t*)data, A, cols, (uint64_t)rank * cols, (uint32_t)n_log,
+                                                                            (uint32_t)d->max_log, d->twiddles, dir == B200_NTT_INVERSE); B200_LAUNCHED(1);
+  B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+  return B200_SUCCESS;
+}
+
+template <class F>
+int ntt_dist_phase2_impl(Domain* d, int field, const void* recv, void* out, int a_log, int b_log, int n_ranks, int dir, cudaStream_t s)
+{
+  if (!d->valid) return B200_INVALID_ARGUMENT;
+  const size_t rows = ((size_t)1 << a_log) / (size_t)n_ranks, B = (size_t)1 << b_log, bcols = B / (size_t)n_ranks;
+  Scratch work;
+  int err;
+  if ((err = work.alloc(rows * B * F::BYTES, s))) return err;
+  // received block r = rows (my k range) x columns of rank r: interleave the blocks into full rows
+  for (int r = 0; r < n_ranks; r++) {
+    B200_CUDA_TRY(cudaMemcpy2DAsync(work.as<uint8_t>() + (size_t)r * bcols * F::BYTES, B * F::BYTES, (const uint8_t*)recv + (size_t)r * rows * bcols * F::BYTES,
+                                    bcols * F::BYTES, bcols * F::BYTES, rows, cudaMemcpyDeviceToDevice, s), B200_COPY_FAILED);
+  }
+  b200_ntt_config c;
+  memset(&c, 0, sizeof(c));
+  c.stream = s;
+  c.batch_size = (int)rows;
+  c.are_inputs_on_device = c.are_outputs_on_device = c.is_async = 1;
+  c.ordering = B200_NN;
+  if ((err = ntt_impl<F>(d, work.p, (int)B, dir, &c, work.p))) return err;
+  b200_vec_ops_config vc;
+  b200_vec_ops_default_config(&vc);
+  vc.stream = s;
+  vc.is_a_on_device = vc.is_result_on_device = vc.is_async = 1;
+  return b200_matrix_transpose(field, work.p, (uint32_t)rows, (uint32_t)B, &vc, out);
+}
+
 extern "C" {
 
 void b200_ntt_default_config(b200_ntt_config* cfg)
@@ -1113,6 +1204,33 @@ __attribute__((visibility("hidden"))) int b200_internal_ntt_domain_root(int fiel
   memcpy(root_out, d->root, (size_t)b200_field_bytes(field));
   *max_log = d->max_log;
   return B200_SUCCESS;
+}
+
+// distributed single NTT, local phases (device-resident slabs; see the comment above k_dist_twiddle)
+static int dist_args_ok(int a_log, int b_log, int n_ranks, int rank)
+{
+  if (a_log < 1 || b_log < 1 || a_log + b_log > 31 || n_ranks < 1 || (n_ranks & (n_ranks - 1)) || rank < 0 || rank >= n_ranks) return 0;
+  return ((1u << a_log) % (unsigned)n_ranks == 0) && ((1u << b_log) % (unsigned)n_ranks == 0);
+}
+int b200_ntt_dist_phase1(int field, void* slab, int a_log, int b_log, int n_ranks, int rank, int dir, void* stream)
+{
+  if (!slab) return B200_INVALID_POINTER;
+  if (field < 0 || field >= B200_FIELD_COUNT || !dist_args_ok(a_log, b_log, n_ranks, rank)) return B200_INVALID_ARGUMENT;
+  Domain* d;
+  int err = get_domain(field, &d);
+  if (err) return err;
+  B200_DISPATCH_NTT_FIELD(field, return ntt_dist_phase1_impl<F>(d, slab, a_log, b_log, n_ranks, rank, dir, (cudaStream_t)stream));
+  return B200_API_NOT_IMPLEMENTED;
+}
+int b200_ntt_dist_phase2(int field, const void* received, void* out_slab, int a_log, int b_log, int n_ranks, int rank, int dir, void* stream)
+{
+  if (!received || !out_slab) return B200_INVALID_POINTER;
+  if (field < 0 || field >= B200_FIELD_COUNT || !dist_args_ok(a_log, b_log, n_ranks, rank)) return B200_INVALID_ARGUMENT;
+  Domain* d;
+  int err = get_domain(field, &d);
+  if (err) return err;
+  B200_DISPATCH_NTT_FIELD(field, return ntt_dist_phase2_impl<F>(d, field, received, out_slab, a_log, b_log, n_ranks, dir, (cudaStream_t)stream));
+  return B200_API_NOT_IMPLEMENTED;
 }
 
 int b200_ntt_extension(int field, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output)

@@ -266,6 +266,17 @@ B200_API int b200_msm_multi_gpu(int curve, const void* scalars, const void* base
 /* batched NTT: batch rows are partitioned; the twiddle domain of the CURRENT device is replicated on the others */
 B200_API int b200_ntt_multi_gpu(int field, const void* input, int size, int dir, const b200_ntt_config* cfg, void* output,
                                 int n_devices, const int* device_ids);
+/* ONE transform spanning several GPUs (the reference stops at one device, multi-device.md:28-36).
+ * N = 2^(a_log+b_log) points viewed as an A x B row-major matrix of the natural-order array; rank r of n_ranks (a power of two
+ * dividing A and B) holds the COLUMN SLAB [A][B/n_ranks] on its device.  phase1 (in place): A-point NTTs down the columns +
+ * the w_N^(col*k) factors; the slab is then n_ranks contiguous blocks of A/n_ranks rows and block s must be delivered to rank
+ * s (all-to-all: NCCL all_to_all_single between processes, peer copies between host threads), each rank receiving its blocks
+ * in source-rank order.  phase2: B-point NTTs along the rows + local transpose -> out_slab = column slab [B][A/n_ranks] of the
+ * B x A view of the natural-order RESULT.  Both directions (the inverse of a forward result takes a_log/b_log swapped).
+ * The domain of the current device must cover N.  b200_ntt_multi_gpu() runs exactly this for a single large host-resident
+ * transform (batch 1), with host-side scatter / gather of the slabs. */
+B200_API int b200_ntt_dist_phase1(int field, void* slab, int a_log, int b_log, int n_ranks, int rank, int dir, void* stream);
+B200_API int b200_ntt_dist_phase2(int field, const void* received, void* out_slab, int a_log, int b_log, int n_ranks, int rank, int dir, void* stream);
 /* the contiguous split both deployments use (threads here, one process per GPU in bench.py): part `index` of `parts` */
 B200_API void b200_shard_range(uint64_t total, int parts, int index, uint64_t* begin, uint64_t* count);
 
@@ -279,7 +290,7 @@ B200_API int b200_get_last_profile(char* names_out, int names_cap, float* ms_out
 
 /* developer / test knobs (msm_pair_levels, msm_pipeline_min, msm_pipeline_chunks, msm_no_pipeline, msm_chunk_target,
  * msm_no_wide_loads, msm_staging_mb, msm_sort, ntt_geom, ntt31_off, ntt_columns_strided, ntt_maxr, ntt_tiles, ntt_maxs,
- * ntt31_two_pass): initialised ONCE from the environment (B200_<NAME>) when the library loads -- the hot path never calls
+ * ntt31_two_pass, copier_threads): initialised ONCE from the environment (B200_<NAME>) when the library loads -- the hot path never calls
  * getenv() -- and changed afterwards only here; value < 0 = unset (built-in policy).  Returns INVALID_ARGUMENT for an unknown name. */
 B200_API int b200_set_tuning(const char* name, int value);
 B200_API int b200_get_tuning(const char* name);

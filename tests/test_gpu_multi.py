@@ -145,3 +145,69 @@ def test_concurrent_host_threads_one_per_device(ref):
         ib.set_device(dv)
         ib.ntt_release_domain(F)
     ib.set_device(0)
+
+
+def _omega(fname, logn):
+    fp = utils.field_params(fname)
+    return pow(fp["rou"], 1 << (fp["two_adicity"] - logn), fp["p"])
+
+
+@pytest.mark.parametrize("fname,field,logn", [("bn254_fr", ib.Field.BN254_FR, 16), ("babybear", ib.Field.BABYBEAR, 19), ("bls12_377_fq", ib.Field.BLS12_377_FQ, 16)])
+def test_single_ntt_spanning_devices(fname, field, logn):
+    """ONE transform over several devices (4-step, one all-to-all by peer copies; b200_ntt_multi_gpu with
+    batch 1) must be bit-identical to the single-device transform, forward and inverse, natural order in and out."""
+    L = utils.field_params(fname)["limbs"]
+    n = 1 << logn
+    ib.set_device(0)
+    ib.ntt_release_domain(field)
+    ib.ntt_init_domain(field, utils.to_limbs([_omega(fname, logn)], L)[0])
+    x = common.seeded_scalars(fname, n, 4242)
+    for k in (2, 4):
+        for d in (ib.NTTDir.kForward, ib.NTTDir.kInverse):
+            exp = ib.ntt(field, x, n, d)
+            got = ib.ntt_multi_gpu(field, x, n, d, device_ids=_devices(k))
+            assert np.array_equal(got, exp), (fname, k, d)
+    for dv in set(_devices(4)):
+        ib.set_device(dv)
+        ib.ntt_release_domain(field)
+    ib.set_device(0)
+
+
+def test_distributed_ntt_phases_with_explicit_all_to_all():
+    """The building blocks the one-process-per-GPU deployment uses (bench.py: phase 1 -> NCCL all_to_all_single -> phase 2),
+    driven here for G = 4 ranks inside one process with the all-to-all done by tensor slicing: column slabs of the A x B view in,
+    column slabs of the B x A view of the natural-order result out; the inverse (dimensions swapped) returns the input."""
+    import torch
+    F, fname = ib.Field.BN254_FR, "bn254_fr"
+    a_log, b_log, G = 7, 6, 4
+    A, B = 1 << a_log, 1 << b_log
+    n = A * B
+    ib.set_device(0)
+    ib.ntt_release_domain(F)
+    ib.ntt_init_domain(F, utils.to_limbs([_omega(fname, a_log + b_log)], 8)[0])
+    x = common.seeded_scalars(fname, n, 77)
+    exp = ib.ntt(F, x, n, ib.NTTDir.kForward)
+
+    def run(vec, a_log, b_log, d):
+        A, B = 1 << a_log, 1 << b_log
+        m = torch.from_numpy(vec.astype(np.int32)).cuda().view(A, B, 8)
+        slabs = [m[:, r * (B // G):(r + 1) * (B // G), :].contiguous() for r in range(G)]
+        for r in range(G):
+            ib.capi.check(ib.capi.lib.b200_ntt_dist_phase1(int(F), slabs[r].data_ptr(), a_log, b_log, G, r, int(d), None), "phase1")
+        torch.cuda.synchronize()
+        blocks = [s.view(G, A // G, B // G, 8) for s in slabs]                       # block s of rank r = rows of rank s
+        outs = []
+        for s_rank in range(G):
+            recv = torch.stack([blocks[r][s_rank] for r in range(G)]).contiguous()     # received in source-rank order
+            out = torch.empty((B, A // G, 8), dtype=torch.int32, device="cuda")
+            ib.capi.check(ib.capi.lib.b200_ntt_dist_phase2(int(F), recv.data_ptr(), out.data_ptr(), a_log, b_log, G, s_rank, int(d), None), "phase2")
+            outs.append(out)
+        torch.cuda.synchronize()
+        full = torch.cat(outs, dim=1).contiguous()                                     # [B][A]: the natural-order result
+        return full.view(-1, 8).cpu().numpy().astype(np.uint32)
+
+    got = run(x, a_log, b_log, ib.NTTDir.kForward)
+    assert np.array_equal(got, exp)
+    back = run(got, b_log, a_log, ib.NTTDir.kInverse)
+    assert np.array_equal(back, x)
+    ib.ntt_release_domain(F)
