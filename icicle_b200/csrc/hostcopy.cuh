@@ -33,6 +33,7 @@ struct CopierCtx {
   cudaStream_t st = nullptr;
   void* slot[2] = {nullptr, nullptr};
   cudaEvent_t slot_free[2] = {nullptr, nullptr};
+  bool used[2] = {false, false}; // slot_free[k] has been recorded at least once (possibly by an EARLIER call still in flight)
 };
 constexpr size_t COPIER_SLOT_BYTES = 4u << 20;
 
@@ -149,10 +150,13 @@ struct PageableCopy {
       const Piece& pc = pieces[i];
       close_chunks_until(pc.chunk);
       const int sl = k & 1;
-      if (k >= 2 && cudaEventSynchronize(c->slot_free[sl]) != cudaSuccess) failed.store(1);
+      // the slot may still be the source of a copy in flight -- from this call or from the previous one (ring_h2d returns
+      // as soon as its copies are issued)
+      if (c->used[sl] && cudaEventSynchronize(c->slot_free[sl]) != cudaSuccess) failed.store(1);
       memcpy(c->slot[sl], pc.src, pc.bytes);
       if (cudaMemcpyAsync(pc.dst, c->slot[sl], pc.bytes, cudaMemcpyHostToDevice, c->st) != cudaSuccess) failed.store(1);
       cudaEventRecord(c->slot_free[sl], c->st);
+      c->used[sl] = true;
       any_in_chunk = true;
       k++;
     }
@@ -257,12 +261,15 @@ inline int ring_d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStrea
       memcpy((uint8_t*)dst_host + mine[sl], c->slot[sl], bsz[sl]);
       full[sl] = false;
     };
+    for (int sl = 0; sl < 2; sl++) // an earlier ring_h2d may still be reading the slots
+      if (c->used[sl] && cudaEventSynchronize(c->slot_free[sl]) != cudaSuccess) failed.store(1);
     for (size_t i = (size_t)t; i < npieces; i += (size_t)T) {
       const int sl = k & 1;
       drain(sl);
       const size_t off = i * COPIER_SLOT_BYTES, b = std::min(COPIER_SLOT_BYTES, bytes - off);
       if (cudaMemcpyAsync(c->slot[sl], (const uint8_t*)src_dev + off, b, cudaMemcpyDeviceToHost, c->st) != cudaSuccess) failed.store(1);
       cudaEventRecord(c->slot_free[sl], c->st);
+      c->used[sl] = true;
       mine[sl] = off; bsz[sl] = b; full[sl] = true;
       drain(sl ^ 1);
       k++;
