@@ -27,11 +27,15 @@ class Field(enum.IntEnum):
     BABYBEAR = 8
     KOALABEAR = 9
     M31 = 10
+    GOLDILOCKS = 11
+    BABYBEAR_EXT4 = 12   # babybear::extension_t (quartic extension): vec-ops; the extension NTT is ntt_extension(Field.BABYBEAR, ...)
+    KOALABEAR_EXT4 = 13
 
 
 FIELD_NAMES = {Field.BN254_FR: "bn254_fr", Field.BN254_FQ: "bn254_fq", Field.BLS12_381_FR: "bls12_381_fr",
                Field.BLS12_381_FQ: "bls12_381_fq", Field.BLS12_377_FR: "bls12_377_fr", Field.BLS12_377_FQ: "bls12_377_fq",
-               Field.BW6_761_FQ: "bw6_761_fq", Field.STARK252: "stark252", Field.BABYBEAR: "babybear", Field.KOALABEAR: "koalabear", Field.M31: "m31"}
+               Field.BW6_761_FQ: "bw6_761_fq", Field.STARK252: "stark252", Field.BABYBEAR: "babybear", Field.KOALABEAR: "koalabear", Field.M31: "m31",
+               Field.GOLDILOCKS: "goldilocks"}
 
 
 class Curve(enum.IntEnum):
@@ -488,6 +492,21 @@ def scalar_sub_vec(field, scalar_a, b, size, config=None, output=None):
 
 def scalar_mul_vec(field, scalar_a, b, size, config=None, output=None):
     return _vec2(field, VecOp.SCALAR_MUL_VEC, scalar_a, b, size, config, output)
+
+
+def ext_mixed_mul(ext_field, a, b, size, config=None, output=None):
+    """extension_vector_mixed_mul (icicle/src/vec_ops.cpp:198-210): a[] in the quartic extension, b[] in the base field."""
+    cfg = copy.copy(config) if config else VecOpsConfig()
+    ap, a_dev, _ka = _ptr(a)
+    bp, b_dev, _kb = _ptr(b)
+    cfg.is_a_on_device, cfg.is_b_on_device = a_dev, b_dev
+    if output is None:
+        output = _out_like(ext_field, size * cfg.batch_size, cfg.is_result_on_device)
+    op, o_dev, _ko = _out_ptr(output)
+    cfg.is_result_on_device = o_dev
+    c = cfg._c()
+    check(lib.b200_ext_mixed_mul(int(ext_field), ap, bp, int(size), C.byref(c), op), "ext_mixed_mul")
+    return output
 
 
 def _unary(fn_name, field_or_curve, a, n_out_elems, limbs, config, output, *extra):

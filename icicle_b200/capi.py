@@ -89,6 +89,7 @@ SYMBOLS = {
     "b200_ecntt": (_i, [_i, _vp, _i, _i, C.POINTER(NttConfigC), _vp]),
     "b200_vec_ops_default_config": (None, [C.POINTER(VecOpsConfigC)]),
     "b200_vec_op": (_i, [_i, _i, _vp, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
+    "b200_ext_mixed_mul": (_i, [_i, _vp, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
     "b200_vector_inv": (_i, [_i, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
     "b200_vector_div": (_i, [_i, _vp, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),
     "b200_vector_sum": (_i, [_i, _vp, _u64, C.POINTER(VecOpsConfigC), _vp]),

@@ -8,6 +8,8 @@
 #include "../../include/icicle_b200.h"
 #include "ff.cuh"
 #include "ext.cuh"
+#include "ext4.cuh"
+#include "goldilocks.cuh"
 #include "ec.cuh"
 
 namespace b200 {
@@ -168,6 +170,12 @@ static inline int num_sms()
     __VA_ARGS__;                                                                                                       \
   } break;
 
+#define B200_EXT4_CASE(ID, PARAMS, ...)                                                                                \
+  case ID: {                                                                                                           \
+    using F = ::b200::Ext4<::b200::params::PARAMS>;                                                                    \
+    __VA_ARGS__;                                                                                                       \
+  } break;
+
 #define B200_DISPATCH_FIELD(field, ...)                                                                                \
   switch (field) {                                                                                                     \
     B200_FIELD_CASE(B200_FIELD_BN254_FR, bn254_fr, __VA_ARGS__)                                                        \
@@ -181,6 +189,9 @@ static inline int num_sms()
     B200_FIELD_CASE(B200_FIELD_BABYBEAR, babybear, __VA_ARGS__)                                                        \
     B200_FIELD_CASE(B200_FIELD_KOALABEAR, koalabear, __VA_ARGS__)                                                      \
     B200_FIELD_CASE(B200_FIELD_M31, m31, __VA_ARGS__)                                                                  \
+    B200_FIELD_CASE(B200_FIELD_GOLDILOCKS, goldilocks, __VA_ARGS__)                                                    \
+    B200_EXT4_CASE(B200_FIELD_BABYBEAR_EXT4, babybear, __VA_ARGS__)                                                    \
+    B200_EXT4_CASE(B200_FIELD_KOALABEAR_EXT4, koalabear, __VA_ARGS__)                                                  \
   default:                                                                                                             \
     return B200_INVALID_ARGUMENT;                                                                                      \
   }
@@ -195,6 +206,7 @@ static inline int num_sms()
     B200_FIELD_CASE(B200_FIELD_STARK252, stark252, __VA_ARGS__)                                                        \
     B200_FIELD_CASE(B200_FIELD_BABYBEAR, babybear, __VA_ARGS__)                                                        \
     B200_FIELD_CASE(B200_FIELD_KOALABEAR, koalabear, __VA_ARGS__)                                                      \
+    B200_FIELD_CASE(B200_FIELD_GOLDILOCKS, goldilocks, __VA_ARGS__)                                                    \
   default:                                                                                                             \
     return B200_API_NOT_IMPLEMENTED;                                                                                   \
   }
@@ -207,6 +219,8 @@ static inline int field_limbs(int field)
   case B200_FIELD_BLS12_381_FQ: case B200_FIELD_BLS12_377_FQ: return 12;
   case B200_FIELD_BW6_761_FQ: return 24;
   case B200_FIELD_BABYBEAR: case B200_FIELD_KOALABEAR: case B200_FIELD_M31: return 1;
+  case B200_FIELD_GOLDILOCKS: return 2;
+  case B200_FIELD_BABYBEAR_EXT4: case B200_FIELD_KOALABEAR_EXT4: return 4;
   default: return 0;
   }
 }

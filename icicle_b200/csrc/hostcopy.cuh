@@ -26,7 +26,7 @@ inline int copier_thread_count()
 {
   const int forced = tune_copier_threads();
   if (forced > 0) return std::min(forced, 32);
-  return (int)std::min<size_t>(12, std::max<unsigned>(2, std::thread::hardware_concurrency() / 8));
+  return (int)std::min<size_t>(8, std::max<unsigned>(2, std::thread::hardware_concurrency() / 8)); // 8 measured best on the 128-core box (profiles/r2_e2e_copier_threads.txt)
 }
 
 struct CopierCtx {

@@ -1169,6 +1169,10 @@ int b200_ntt_get_root_of_unity_from_domain(int field, uint64_t logn, void* rou_o
     uint32_t host_m[F::N];
     B200_CUDA_TRY(cudaMemcpy(host_m, src, F::BYTES, cudaMemcpyDeviceToHost), B200_COPY_FAILED);
     // the table is kept in Montgomery form; hand back the reference's standard form
+    if (field == B200_FIELD_GOLDILOCKS) { // no internal Montgomery domain (goldilocks.cuh)
+      memcpy(rou_out, host_m, F::BYTES);
+      return B200_SUCCESS;
+    }
     b200_vec_ops_config vc;
     b200_vec_ops_default_config(&vc);
     return b200_convert_montgomery(field, host_m, 1, 0, &vc, rou_out);

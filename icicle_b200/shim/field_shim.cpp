@@ -111,6 +111,70 @@ namespace {
     return to_err(b200_matrix_transpose(FIELD, in, rows, cols, &c, out));
   }
 
+#if defined(EXT_FIELD) && (FIELD_ID == BABY_BEAR || FIELD_ID == KOALA_BEAR)
+  #define B200_HAS_EXT4 1
+  // REGISTER_*_EXT_FIELD_BACKEND family (vec_ops_backend.h:297-494): the same C-ABI entry points with the extension's field id
+  constexpr int EXT = ext_field_id();
+  static_assert(sizeof(extension_t) == 4 * sizeof(scalar_t), "quartic extension");
+  template <int OP>
+  eIcicleError ext_vec2(const Device&, const extension_t* a, const extension_t* b, uint64_t size, const VecOpsConfig& config, extension_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_vec_op(EXT, OP, a, b, size, &c, out));
+  }
+  eIcicleError ext_accumulate(const Device&, extension_t* a, const extension_t* b, uint64_t size, const VecOpsConfig& config)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_vec_op(EXT, B200_VEC_ACCUMULATE, a, b, size, &c, a));
+  }
+  eIcicleError ext_mixed_mul(const Device&, const extension_t* a, const scalar_t* b, uint64_t size, const VecOpsConfig& config, extension_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_ext_mixed_mul(EXT, a, b, size, &c, out));
+  }
+  eIcicleError ext_inv(const Device&, const extension_t* a, uint64_t size, const VecOpsConfig& config, extension_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_vector_inv(EXT, a, size, &c, out));
+  }
+  eIcicleError ext_div(const Device&, const extension_t* a, const extension_t* b, uint64_t size, const VecOpsConfig& config, extension_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_vector_div(EXT, a, b, size, &c, out));
+  }
+  eIcicleError ext_sum(const Device&, const extension_t* a, uint64_t size, const VecOpsConfig& config, extension_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_vector_sum(EXT, a, size, &c, out));
+  }
+  eIcicleError ext_product(const Device&, const extension_t* a, uint64_t size, const VecOpsConfig& config, extension_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_vector_product(EXT, a, size, &c, out));
+  }
+  eIcicleError ext_convert_mont(const Device&, const extension_t* in, uint64_t size, bool is_into, const VecOpsConfig& config, extension_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_convert_montgomery(EXT, in, size, is_into, &c, out));
+  }
+  eIcicleError ext_bit_rev(const Device&, const extension_t* in, uint64_t size, const VecOpsConfig& config, extension_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_bit_reverse(EXT, in, size, &c, out));
+  }
+  eIcicleError ext_slice(const Device&, const extension_t* in, uint64_t offset, uint64_t stride, uint64_t size_in, uint64_t size_out,
+                         const VecOpsConfig& config, extension_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_slice(EXT, in, offset, stride, size_in, size_out, &c, out));
+  }
+  eIcicleError ext_transpose(const Device&, const extension_t* in, uint32_t rows, uint32_t cols, const VecOpsConfig& config, extension_t* out)
+  {
+    b200_vec_ops_config c = to_c(config);
+    return to_err(b200_matrix_transpose(EXT, in, rows, cols, &c, out));
+  }
+#endif
+
 #ifdef NTT
   b200_ntt_config to_c(const NTTConfig<scalar_t>& config)
   {
@@ -177,6 +241,24 @@ REGISTER_CONVERT_MONTGOMERY_BACKEND(B200_DEVICE_TYPE, convert_mont);
 REGISTER_BIT_REVERSE_BACKEND(B200_DEVICE_TYPE, bit_rev);
 REGISTER_SLICE_BACKEND(B200_DEVICE_TYPE, slice_op);
 REGISTER_MATRIX_TRANSPOSE_BACKEND(B200_DEVICE_TYPE, transpose);
+#ifdef B200_HAS_EXT4
+REGISTER_VECTOR_ADD_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_vec2<B200_VEC_ADD>);
+REGISTER_VECTOR_SUB_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_vec2<B200_VEC_SUB>);
+REGISTER_VECTOR_MUL_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_vec2<B200_VEC_MUL>);
+REGISTER_VECTOR_ACCUMULATE_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_accumulate);
+REGISTER_VECTOR_MIXED_MUL_BACKEND(B200_DEVICE_TYPE, ext_mixed_mul);
+REGISTER_VECTOR_DIV_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_div);
+REGISTER_VECTOR_INV_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_inv);
+REGISTER_SCALAR_ADD_VEC_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_vec2<B200_SCALAR_ADD_VEC>);
+REGISTER_SCALAR_SUB_VEC_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_vec2<B200_SCALAR_SUB_VEC>);
+REGISTER_SCALAR_MUL_VEC_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_vec2<B200_SCALAR_MUL_VEC>);
+REGISTER_VECTOR_SUM_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_sum);
+REGISTER_VECTOR_PRODUCT_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_product);
+REGISTER_CONVERT_MONTGOMERY_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_convert_mont);
+REGISTER_MATRIX_TRANSPOSE_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_transpose);
+REGISTER_BIT_REVERSE_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_bit_rev);
+REGISTER_SLICE_EXT_FIELD_BACKEND(B200_DEVICE_TYPE, ext_slice);
+#endif
 #ifdef NTT
 REGISTER_NTT_BACKEND(B200_DEVICE_TYPE, ntt_impl);
   #ifdef EXT_FIELD

@@ -59,6 +59,20 @@ namespace b200_shim {
     return B200_FIELD_KOALABEAR;
 #elif FIELD_ID == M31
     return B200_FIELD_M31;
+#elif FIELD_ID == GOLDILOCKS
+    return B200_FIELD_GOLDILOCKS;
+#else
+    return -1;
+#endif
+  }
+
+  // quartic extension of the build's scalar field (EXT_FIELD builds of babybear / koalabear), -1 if we have none
+  constexpr int ext_field_id()
+  {
+#if FIELD_ID == BABY_BEAR
+    return B200_FIELD_BABYBEAR_EXT4;
+#elif FIELD_ID == KOALA_BEAR
+    return B200_FIELD_KOALABEAR_EXT4;
 #else
     return -1;
 #endif

@@ -61,6 +61,9 @@ typedef enum {
   B200_FIELD_BABYBEAR = 8,     /* fields/stark_fields/babybear.h */
   B200_FIELD_KOALABEAR = 9,    /* fields/stark_fields/koalabear.h */
   B200_FIELD_M31 = 10,         /* fields/stark_fields/m31.h: vec-ops only (no NTT upstream); Montgomery form == standard form (m31.h:232-234) */
+  B200_FIELD_GOLDILOCKS = 11,  /* fields/stark_fields/goldilocks.h: p = 2^64 - 2^32 + 1, 2 limbs, NTT + vec-ops */
+  B200_FIELD_BABYBEAR_EXT4 = 12,  /* babybear::extension_t  = QuarticExtensionField (fields/quartic_extension.h), 4 limbs: vec-ops; */
+  B200_FIELD_KOALABEAR_EXT4 = 13, /* koalabear::extension_t   its NTT is b200_ntt_extension on the BASE field id */
   B200_FIELD_COUNT
 } b200_field_t;
 
@@ -218,6 +221,10 @@ typedef enum {
 B200_API void b200_vec_ops_default_config(b200_vec_ops_config* cfg);
 /* element-wise op over size*batch_size elements (scalar_* ops: `a` holds one scalar per batch, cpu_vec_ops.cpp:325-341) */
 B200_API int b200_vec_op(int field, int op, const void* a, const void* b, uint64_t size, const b200_vec_ops_config* cfg, void* out);
+/* extension_vector_mixed_mul (vec_ops_backend.h:284-290,346; cpu_vec_ops.cpp): out[i] = a[i] * b[i] with a[] in the quartic extension
+ * `ext_field` (B200_FIELD_*_EXT4) and b[] in its base field.  Every other extension vec-op (REGISTER_*_EXT_FIELD_BACKEND,
+ * vec_ops_backend.h:297-494) is the ordinary entry point called with the extension's field id. */
+B200_API int b200_ext_mixed_mul(int ext_field, const void* a, const void* b, uint64_t size, const b200_vec_ops_config* cfg, void* out);
 /* vector_inv / vector_div: out = a^-1, out = a / b element-wise; inverse(0) = 0 like the reference (modular_arithmetic.h:621-623)
  * REGISTER_VECTOR_INV_BACKEND / REGISTER_VECTOR_DIV_BACKEND (vec_ops_backend.h:107,136); cpu_vec_ops.cpp:386-403 */
 B200_API int b200_vector_inv(int field, const void* a, uint64_t size, const b200_vec_ops_config* cfg, void* out);

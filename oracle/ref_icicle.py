@@ -34,6 +34,7 @@ TARGETS = {
     "koalabear": dict(curve=False, s=1),
     "stark252": dict(curve=False, s=8),
     "m31": dict(curve=False, s=1),
+    "goldilocks": dict(curve=False, s=2),
 }
 
 

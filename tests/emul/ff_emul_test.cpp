@@ -8,6 +8,8 @@
 #define __host__
 #define __device__
 #include "../../icicle_b200/csrc/ff.cuh"
+#include "../../icicle_b200/csrc/goldilocks.cuh"
+#include "../../icicle_b200/csrc/ext4.cuh"
 using namespace b200;
 
 template <class F> static F parse(const std::string& h)
@@ -32,6 +34,14 @@ template <class F> static void run(const std::string& sa, const std::string& sb)
   print(a + b); print(a - b); print(a * b); print(a.to_mont()); print(a.from_mont()); print(a.neg());
   printf("\n");
 }
+// quartic extension: a+b, a-b, a*b (coefficient products are Montgomery products: true product / R), to_mont, from_mont, and the
+// true inverse computed in the Montgomery domain (fermat_inv_mont) -- 0 -> 0
+template <class E> static void run_ext(const std::string& sa, const std::string& sb)
+{
+  E a = parse<E>(sa), b = parse<E>(sb);
+  print(a + b); print(a - b); print(a * b); print(a.to_mont()); print(a.from_mont()); print(fermat_inv_mont(a.to_mont()).from_mont());
+  printf("\n");
+}
 int main()
 {
   std::string f, a, b;
@@ -47,6 +57,9 @@ int main()
     else if (f == "babybear") run<Fp<params::babybear>>(a, b);
     else if (f == "koalabear") run<Fp<params::koalabear>>(a, b);
     else if (f == "m31") run<Fp<params::m31>>(a, b);
+    else if (f == "goldilocks") run<Fp<params::goldilocks>>(a, b);
+    else if (f == "ext4_babybear") run_ext<Ext4<params::babybear>>(a, b);
+    else if (f == "ext4_koalabear") run_ext<Ext4<params::koalabear>>(a, b);
     else { printf("unknown\n"); }
   }
   return 0;

@@ -73,7 +73,8 @@ def test_msm_golden(name, curve, g2curve, fq, L):
 
 @pytest.mark.parametrize("name,field,fname", [("bn254", ib.Field.BN254_FR, "bn254_fr"), ("bls12_381", ib.Field.BLS12_381_FR, "bls12_381_fr"),
                                               ("babybear", ib.Field.BABYBEAR, "babybear"), ("bls12_377", ib.Field.BLS12_377_FR, "bls12_377_fr"),
-                                              ("bw6_761", ib.Field.BLS12_377_FQ, "bls12_377_fq"), ("stark252", ib.Field.STARK252, "stark252")])
+                                              ("bw6_761", ib.Field.BLS12_377_FQ, "bls12_377_fq"), ("stark252", ib.Field.STARK252, "stark252"),
+                                              ("goldilocks", ib.Field.GOLDILOCKS, "goldilocks")])
 def test_ntt_and_vec_golden(name, field, fname):
     """NTT (all orderings, cosets, column batch, both directions) and vec-ops of every NTT field of the north-star list
     against ITS OWN reference build's outputs; bw6_761's scalar field is the 12-limb bls12_377 base field."""
@@ -203,3 +204,70 @@ def test_grumpkin_scalar_vec_ops_golden():
     assert np.array_equal(ib.vector_add(field, a, b, 50), g["vec_add"].reshape(-1, L))
     assert np.array_equal(ib.vector_sub(field, a, b, 50), g["vec_sub"].reshape(-1, L))
     assert np.array_equal(ib.vector_mul(field, a, b, 50), g["vec_mul"].reshape(-1, L))
+
+
+@pytest.mark.parametrize("name,ext,base", [("babybear", ib.Field.BABYBEAR_EXT4, ib.Field.BABYBEAR), ("koalabear", ib.Field.KOALABEAR_EXT4, ib.Field.KOALABEAR)])
+def test_extension_vec_ops_golden(name, ext, base):
+    """the REGISTER_*_EXT_FIELD_BACKEND family (vec_ops_backend.h:297-494) on the quartic extension of BabyBear /
+    KoalaBear -- the ordinary C-ABI entry points with the extension's field id + b200_ext_mixed_mul -- bit-exact against the
+    reference's own `<field>_extension_*` outputs (tests/golden/<field>_ext_ops.npz), host and device buffers."""
+    g = gold(f"{name}_ext_ops")
+    a, b, s = g["a"], g["b"], g["s"]
+    n3 = a.shape[0]
+    n, batch = n3 // 3, 3
+    for dev in (False, True):
+        A, B, S = (ib.to_device(a), ib.to_device(b), ib.to_device(s)) if dev else (a, b, s)
+        h = (lambda x: ib.to_host(x).reshape(-1, 4)) if dev else (lambda x: x)
+        cfg = lambda **kw: ib.VecOpsConfig(is_result_on_device=dev, **kw)
+        assert np.array_equal(h(ib.vector_add(ext, A, B, n3, cfg())), g["vector_add"])
+        assert np.array_equal(h(ib.vector_sub(ext, A, B, n3, cfg())), g["vector_sub"])
+        assert np.array_equal(h(ib.vector_mul(ext, A, B, n3, cfg())), g["vector_mul"])
+        assert np.array_equal(h(ib.vector_div(ext, A, B, n3, cfg())), g["vector_div"])
+        assert np.array_equal(h(ib.vector_inv(ext, B, n3, cfg())), g["vector_inv"])
+        assert np.array_equal(h(ib.ext_mixed_mul(ext, A, S, n3, cfg())), g["vector_mixed_mul"])
+        acc = ib.to_device(a) if dev else a.copy()
+        ib.vector_accumulate(ext, acc, B, n3)
+        assert np.array_equal(h(acc), g["vector_accumulate"])
+        for columns, tag in ((False, "rows"), (True, "cols")):
+            sc = ib.to_device(a[:batch].copy()) if dev else a[:batch].copy()
+            c2 = lambda: cfg(batch_size=batch, columns_batch=columns)
+            assert np.array_equal(h(ib.scalar_add_vec(ext, sc, B, n, c2())), g[f"scalar_add_vec_{tag}"])
+            assert np.array_equal(h(ib.scalar_sub_vec(ext, sc, B, n, c2())), g[f"scalar_sub_vec_{tag}"])
+            assert np.array_equal(h(ib.scalar_mul_vec(ext, sc, B, n, c2())), g[f"scalar_mul_vec_{tag}"])
+            assert np.array_equal(h(ib.vector_sum(ext, A, n, c2())), g[f"vector_sum_{tag}"])
+            assert np.array_equal(h(ib.vector_product(ext, A, n, c2())), g[f"vector_product_{tag}"])
+        assert np.array_equal(h(ib.convert_montgomery(ext, A, n3, True, cfg())), g["convert_montgomery_1"])
+        assert np.array_equal(h(ib.convert_montgomery(ext, A, n3, False, cfg())), g["convert_montgomery_0"])
+        a32 = ib.to_device(a[:32].copy()) if dev else a[:32].copy()
+        a48 = ib.to_device(a[:48].copy()) if dev else a[:48].copy()
+        assert np.array_equal(h(ib.bit_reverse(ext, a32, 32, cfg())), g["bit_reverse"])
+        assert np.array_equal(h(ib.matrix_transpose(ext, a48, 6, 8, cfg())), g["matrix_transpose_6x8"])
+        assert np.array_equal(h(ib.slice(ext, a48, 3, 4, 48, 10, cfg())), g["slice_3_4_10"])
+
+
+def test_goldilocks_montgomery_conversion_and_large_ntt():
+    """Goldilocks (p = 2^64 - 2^32 + 1) has no internal Montgomery domain on the device: the API-level conversion must still be
+    x * 2^(+-64) mod p (fields/params_gen.h:35-50), and a 2^18 transform must round-trip and match the defining sum at a few outputs."""
+    F = ib.Field.GOLDILOCKS
+    fp = utils.field_params("goldilocks")
+    p = fp["p"]
+    x = common.seeded_scalars("goldilocks", 1000, 5)
+    xi = utils.from_limbs(x)
+    assert utils.from_limbs(ib.convert_montgomery(F, x, 1000, True)) == [v * (1 << 64) % p for v in xi]
+    assert utils.from_limbs(ib.convert_montgomery(F, x, 1000, False)) == [v * pow(1 << 64, -1, p) % p for v in xi]
+    logn = 18
+    n = 1 << logn
+    w = pow(fp["rou"], 1 << (fp["two_adicity"] - logn), p)
+    ib.ntt_release_domain(F)
+    ib.ntt_init_domain(F, utils.to_limbs([w], 2)[0])
+    assert utils.from_limbs(ib.get_root_of_unity_from_domain(F, logn).reshape(1, 2))[0] == w
+    v = common.seeded_scalars("goldilocks", n, 6)
+    V = ib.ntt(F, v, n, ib.NTTDir.kForward)
+    assert np.array_equal(ib.ntt(F, V, n, ib.NTTDir.kInverse), v)
+    sp = np.zeros((n, 2), dtype=np.uint32)
+    a_idx, b_idx, alpha, beta = 4321, n - 3, 0x123456789ABCDEF, 11
+    sp[a_idx], sp[b_idx] = utils.to_limbs([alpha], 2)[0], utils.to_limbs([beta], 2)[0]
+    S = ib.ntt(F, sp, n, ib.NTTDir.kForward)
+    for k in (0, 1, 77777, n - 1):
+        assert utils.from_limbs(S[k:k + 1])[0] == (alpha * pow(w, a_idx * k, p) + beta * pow(w, b_idx * k, p)) % p
+    ib.ntt_release_domain(F)

@@ -80,6 +80,8 @@ def test_port_ntt_and_vec_vs_golden(name, field):
 def test_port_field_arithmetic_all_fields():
     rng = random.Random(11)
     for name in utils.PARAMS["fields"]:
+        if name == "goldilocks":
+            continue  # special-form field with its own arithmetic upstream (goldilocks.h), not the generic Barrett path the port restates
         p = utils.field_params(name)["p"]
         a = [rng.randrange(p) for _ in range(100)] + [0, p - 1, p - 1]
         b = [rng.randrange(p) for _ in range(100)] + [0, p - 1, 1]
@@ -264,3 +266,76 @@ def test_ecntt_golden_vs_definition():
     for b in range(batch):
         y = transform([pts[i * batch + b] for i in range(n)], False, 1)
         assert y == [exp[i * batch + b] for i in range(n)], b
+
+
+def _ext4(name):
+    fp = utils.field_params(name)
+    p, nr = fp["p"], fp["nonresidue"]
+
+    def mul(x, y):
+        c = [0] * 8
+        for i in range(4):
+            for j in range(4):
+                c[i + j] += x[i] * y[j]
+        return [(c[k] + nr * c[k + 4]) % p for k in range(4)]
+    return p, mul
+
+
+@pytest.mark.parametrize("name", ["babybear", "koalabear"])
+def test_extension_vec_ops_golden_vs_integers(name):
+    """tests/golden/<field>_ext_ops.npz (tools/make_golden_extops.py, the reference's `<field>_extension_*` vec-ops) against
+    first-principles arithmetic in F_p[x]/(x^4 - nr) on Python integers: pins the fixtures the GPU extension vec-ops are tested
+    with (quartic_extension.h:182-199 product, :246-283 inverse, :78-88 coefficient-wise Montgomery form)."""
+    g = _gold(f"{name}_ext_ops")
+    p, mul = _ext4(name)
+    a, b, s = g["a"].astype(object), g["b"].astype(object), [int(v) for v in g["s"].reshape(-1)]
+    rows = lambda arr: [[int(v) for v in r] for r in arr]
+    A, B = rows(a), rows(b)
+    assert rows(g["vector_add"]) == [[(x + y) % p for x, y in zip(u, v)] for u, v in zip(A, B)]
+    assert rows(g["vector_sub"]) == [[(x - y) % p for x, y in zip(u, v)] for u, v in zip(A, B)]
+    assert rows(g["vector_accumulate"]) == rows(g["vector_add"])
+    assert rows(g["vector_mul"]) == [mul(u, v) for u, v in zip(A, B)]
+    assert rows(g["vector_mixed_mul"]) == [[x * k % p for x in u] for u, k in zip(A, s)]
+    inv = rows(g["vector_inv"])
+    for v, iv in zip(B, inv):
+        assert (mul(v, iv) == [1, 0, 0, 0]) if any(v) else (iv == [0, 0, 0, 0])
+    assert rows(g["vector_div"]) == [mul(u, iv) for u, iv in zip(A, inv)]
+    n, batch = len(A) // 3, 3
+    for tag, idx in (("rows", lambda bi, i: bi * n + i), ("cols", lambda bi, i: i * batch + bi)):
+        add, sub_, mul_ = rows(g[f"scalar_add_vec_{tag}"]), rows(g[f"scalar_sub_vec_{tag}"]), rows(g[f"scalar_mul_vec_{tag}"])
+        sm, pr = rows(g[f"vector_sum_{tag}"]), rows(g[f"vector_product_{tag}"])
+        for bi in range(batch):
+            acc_s, acc_p = [0, 0, 0, 0], [1, 0, 0, 0]
+            for i in range(n):
+                t = idx(bi, i)
+                assert add[t] == [(x + y) % p for x, y in zip(A[bi], B[t])]
+                assert sub_[t] == [(x - y) % p for x, y in zip(A[bi], B[t])]
+                assert mul_[t] == mul(A[bi], B[t])
+                acc_s = [(x + y) % p for x, y in zip(acc_s, A[t])]
+                acc_p = mul(acc_p, A[t])
+            assert sm[bi] == acc_s and pr[bi] == acc_p
+    R = 1 << 32
+    assert rows(g["convert_montgomery_1"]) == [[x * R % p for x in u] for u in A]
+    assert rows(g["convert_montgomery_0"]) == [[x * pow(R, -1, p) % p for x in u] for u in A]
+    assert rows(g["bit_reverse"]) == [A[common.bitrev(i, 5)] for i in range(32)]
+    assert rows(g["matrix_transpose_6x8"]) == [A[r * 8 + c] for c in range(8) for r in range(6)]
+    assert rows(g["slice_3_4_10"]) == [A[3 + 4 * i] for i in range(10)]
+
+
+def test_goldilocks_golden_vs_defining_sum():
+    """tests/golden/goldilocks.npz (reference build of the special-form field) against the defining DFT sums and plain integer
+    arithmetic: pins the fixture the GPU Goldilocks path is tested with (the C port does not cover this field)."""
+    g = _gold("goldilocks")
+    fp = utils.field_params("goldilocks")
+    p = fp["p"]
+    n = 64
+    root = utils.from_limbs(g["ntt_root"].reshape(1, -1))[0]
+    w = pow(root, 4, p)
+    x = utils.from_limbs(g["ntt_input"])
+    assert utils.from_limbs(g["ntt_d0_o0"]) == common.ntt_naive_ints(x[:n], w, p)
+    assert utils.from_limbs(g["ntt_d1_o0"]) == common.ntt_naive_ints(x[:n], w, p, inverse=True)
+    gc = utils.from_limbs(g["coset_arb"].reshape(1, -1))[0]
+    assert utils.from_limbs(g["ntt_d0_coset_arb"]) == common.ntt_naive_ints(x[:n], w, p, coset=gc)
+    a, b = utils.from_limbs(g["vec_a"]), utils.from_limbs(g["vec_b"])
+    assert utils.from_limbs(g["vec_mul"]) == [u * v % p for u, v in zip(a, b)]
+    assert utils.from_limbs(g["vec_add"]) == [(u + v) % p for u, v in zip(a, b)]
