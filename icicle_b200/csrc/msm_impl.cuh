@@ -32,6 +32,7 @@
 #pragma once
 #include "common.cuh"
 #include "msm_pairs.cuh"
+#include "msm_sort.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cstdlib>
@@ -130,6 +131,55 @@ __global__ void __launch_bounds__(256) k_digits(
   }
 }
 
+// K6 + ranking (msm_sort.cuh): as k_digits, but every non-zero digit also takes its rank inside its bucket with one returning
+// atomicAdd on the bucket counter; zero digits are marked dropped.  rank word = rank | sign bit of the digit.
+template <class S>
+__global__ void __launch_bounds__(256) k_digits_rank(
+  const uint32_t* __restrict__ scalars, uint32_t n, uint32_t batch_local, MsmPlan pl, bool scalars_mont, uint32_t* __restrict__ keys,
+  uint32_t* __restrict__ ranks, uint32_t* __restrict__ cnt)
+{
+  uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (uint64_t)n * batch_local) return;
+  const uint32_t b = (uint32_t)(g / n), i = (uint32_t)(g % n);
+  S s = load_fp<S>(scalars + g * S::N);
+  if (scalars_mont) s = s.from_mont();
+  const uint32_t c = pl.c, half = 1u << (c - 1), full = 1u << c;
+  uint32_t carry = 0;
+  const uint64_t ent_base = (uint64_t)b * pl.nwin * n;
+  for (int w = 0; w < pl.nwin; w++) {
+    const uint32_t lsb = w * c;
+    uint32_t raw = 0;
+    if (lsb < (uint32_t)pl.bits) {
+      const uint32_t limb = lsb >> 5, off = lsb & 31;
+      uint64_t two = s.v[limb];
+      if (limb + 1 < S::N) two |= (uint64_t)s.v[limb + 1] << 32;
+      raw = (uint32_t)(two >> off) & (full - 1);
+      const uint32_t avail = pl.bits - lsb;
+      if (avail < c) raw &= (1u << avail) - 1;
+    }
+    raw += carry;
+    uint32_t mag, neg;
+    if (raw > half) {
+      mag = full - raw;
+      neg = SORT_SIGN_BIT;
+      carry = 1;
+    } else {
+      mag = raw;
+      neg = 0;
+      carry = 0;
+    }
+    const uint32_t bm = w % pl.nbm;
+    uint32_t key = SORT_DROPPED, rk = 0;
+    if (mag) {
+      key = (b * pl.nbm + bm) * half + (mag - 1);
+      rk = atomicAdd(cnt + key, 1u) | neg;
+    }
+    const uint64_t e = ent_base + (uint64_t)w * n + i;
+    keys[e] = key;
+    ranks[e] = rk;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // K8: slice accumulation over the sorted entries.
 // partial slot layout: pkey[2*t + {0,1}] (0xffffffff = empty), pflag bit0 = run starts in this slice, bit1 = run ends here.
@@ -148,7 +198,7 @@ __global__ void __launch_bounds__(MSM_THREADS) k_accumulate(
   constexpr int AW = 2 * F::N, XW = 4 * F::N;
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_slices) return;
-  if (DIRECT) n_entries = *n_dev;
+  if (n_dev) n_entries = *n_dev; // the live entry count is only known on the device (pair levels; counting sort: off[nb])
   const uint64_t beg = t * slice;
   const uint64_t end = (beg + slice < n_entries) ? beg + slice : n_entries;
   pkey[2 * t] = P_EMPTY;
@@ -515,18 +565,27 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
 
   if (ext_bkt && (batch != 1 || chunk != 1)) return B200_INVALID_ARGUMENT;
   const bool do_acc = (phases & MSM_ACC) != 0, do_red = (phases & MSM_RED) != 0;
-  Scratch s_k0, s_k1, s_v0, s_v1, s_cub, s_bkt, s_pkey, s_pflag, s_ppt, s_pkey2, s_pflag2, s_ppt2, s_red0, s_red1;
+  Scratch s_k0, s_k1, s_v0, s_v1, s_cub, s_bkt, s_pkey, s_pflag, s_ppt, s_pkey2, s_pflag2, s_ppt2, s_red0, s_red1, s_cnt0, s_off0;
+  ScanScratch scan_sc;
   size_t cub_bytes = 0;
+  // bucket grouping: cub radix sort for large entry lists, the counting sort of msm_sort.cuh below 2^25 entries (on par / fewer
+  // launches there; at 2^26 points its fully scattered stores lose 47 vs 21 ms: profiles/r2_msm_counting_sort_experiment.txt).
+  // msm_sort knob: 1 = always cub, 2 = always counting sort.
+  const bool use_cub = tune(T_MSM_SORT) == 1 || (tune(T_MSM_SORT) != 2 && max_ent > (1ull << 25));
   if (do_acc) {
     if ((err = s_k0.alloc(max_ent * 4, s))) return err;
     if ((err = s_k1.alloc(max_ent * 4, s))) return err;
     if ((err = s_v0.alloc(max_ent * 4, s))) return err;
     if ((err = s_v1.alloc(max_ent * 4, s))) return err;
-    {
+    if (use_cub) {
       cub::DoubleBuffer<uint32_t> dk(s_k0.as<uint32_t>(), s_k1.as<uint32_t>()), dv(s_v0.as<uint32_t>(), s_v1.as<uint32_t>());
       cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, dk, dv, (int64_t)max_ent, 0, 32, s);
+      if ((err = s_cub.alloc(cub_bytes, s))) return err;
+    } else {
+      if ((err = s_cnt0.alloc((size_t)(max_buckets + 1) * 4, s))) return err;
+      if ((err = s_off0.alloc((size_t)(max_buckets + 1) * 4, s))) return err;
     }
-    if ((err = s_cub.alloc(cub_bytes, s))) return err;
+    if ((err = scan_sc.prepare(max_buckets + 1, s))) return err;
     if ((err = s_pkey.alloc(max_slices * 2 * 4, s))) return err;
     if ((err = s_pflag.alloc(max_slices * 2 * 4, s))) return err;
     if ((err = s_ppt.alloc(max_slices * 2 * XW * 4, s))) return err;
@@ -549,13 +608,11 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
   uint64_t cap[10];
   cap[0] = max_ent;
   for (int l = 0; l < levels; l++) cap[l + 1] = cap[l] / 2 + nb_max + 1;
-  Scratch s_off[2], s_cnt, s_scan, s_lvl[2], s_lkey[2], s_pbuf, s_tree, s_tpre;
-  size_t scan_bytes = 0;
+  Scratch s_off[2], s_cnt, s_lvl[2], s_lkey[2], s_pbuf, s_tree, s_tpre;
   uint64_t tree_m[8];
   int tree_levels = 0;
   uint64_t tree_total = 0;
   if (levels > 0) {
-    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(nb_max + 1), s);
     uint64_t cap_max = cap[0]; // sparse lists (few entries, many buckets) have a growing upper bound
     for (int l = 1; l < levels; l++) cap_max = std::max(cap_max, cap[l]);
     uint64_t m = (((cap_max + 1) / 2 + (uint64_t)PAIR_J * PAIR_THREADS - 1) / ((uint64_t)PAIR_J * PAIR_THREADS)) * PAIR_THREADS;
@@ -573,13 +630,13 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
         ok = ok && !s_lkey[b].alloc((size_t)cap[b + 1] * 4, s);
       }
     }
-    ok = ok && !s_cnt.alloc(((size_t)nb_max + 1) * 4, s) && !s_scan.alloc(scan_bytes, s) &&
+    ok = ok && !s_cnt.alloc(((size_t)nb_max + 1) * 4, s) &&
          !s_pbuf.alloc(((size_t)cap[0] / 2 + 1) * F::BYTES, s) && !s_tree.alloc((size_t)tree_total * F::BYTES, s) &&
          !s_tpre.alloc((size_t)tree_total * F::BYTES, s);
     if (!ok) { // not enough memory for the level buffers: fall back to the XYZZ-only schedule
       levels = 0;
       for (int b = 0; b < 2; b++) { s_off[b].release(); s_lvl[b].release(); s_lkey[b].release(); }
-      s_cnt.release(); s_scan.release(); s_pbuf.release(); s_tree.release(); s_tpre.release();
+      s_cnt.release(); s_pbuf.release(); s_tree.release(); s_tpre.release();
     }
   }
   if (levels > 0) {
@@ -599,36 +656,59 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
     const bool pts_wide = (((uintptr_t)pts) & 31u) == 0 && (F::BYTES % 32 == 0) && tune(T_MSM_NO_WIDE_LOADS) <= 0;
 
     if (do_acc) {
-    // K6
-    {
+    const uint32_t nb = (uint32_t)n_buckets;
+    const uint32_t* sorted_k;          // entries grouped by bucket: keys ...
+    const uint32_t* sorted_v;          // ... and (point index | sign)
+    const uint32_t* n_live = nullptr;  // device word holding the number of live entries (counting sort), or nullptr = n_ent
+    uint32_t* off_first = (levels > 0) ? s_off[0].as<uint32_t>() : s_off0.as<uint32_t>(); // off[k] = first entry of bucket k
+    uint32_t acc_sentinel = sentinel;
+    if (use_cub) {
+      // K6 + K7 (round 1): digits with a sentinel key for zero digits, library radix sort
       uint64_t th = (uint64_t)n * bl;
       k_digits<S><<<(unsigned)((th + 255) / 256), 256, 0, s>>>(
         sc, n, (uint32_t)bl, pl, cfg->are_scalars_montgomery_form, shared, s_k0.as<uint32_t>(), s_v0.as<uint32_t>(), sentinel); B200_LAUNCHED(1);
       B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
-    }
-    prof.mark("digits");
-    // K7
-    cub::DoubleBuffer<uint32_t> dk(s_k0.as<uint32_t>(), s_k1.as<uint32_t>()), dv(s_v0.as<uint32_t>(), s_v1.as<uint32_t>());
-    {
+      prof.mark("digits");
+      cub::DoubleBuffer<uint32_t> dk(s_k0.as<uint32_t>(), s_k1.as<uint32_t>()), dv(s_v0.as<uint32_t>(), s_v1.as<uint32_t>());
       const int key_bits = std::max(1, ilog2_ceil((uint64_t)sentinel + 1));
       B200_CUDA_TRY(cub::DeviceRadixSort::SortPairs(s_cub.p, cub_bytes, dk, dv, (int64_t)n_ent, 0, key_bits, s), B200_UNKNOWN_ERROR);
+      sorted_k = dk.Current();
+      sorted_v = dv.Current();
+      if (levels > 0) {
+        k_bounds<<<(nb + 1 + 255) / 256, 256, 0, s>>>(sorted_k, (uint32_t)n_ent, nb, off_first); B200_LAUNCHED(1);
+      }
+      prof.mark("sort");
+    } else {
+      // K6 + K7 (msm_sort.cuh): digits ranked inside their bucket by one atomic each, scan of the counters, scatter
+      B200_CUDA_TRY(cudaMemsetAsync(s_cnt0.p, 0, ((size_t)nb + 1) * 4, s), B200_UNKNOWN_ERROR);
+      uint64_t th = (uint64_t)n * bl;
+      k_digits_rank<S><<<(unsigned)((th + 255) / 256), 256, 0, s>>>(
+        sc, n, (uint32_t)bl, pl, cfg->are_scalars_montgomery_form, s_k0.as<uint32_t>(), s_v0.as<uint32_t>(), s_cnt0.as<uint32_t>()); B200_LAUNCHED(1);
+      B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+      prof.mark("digits");
+      if ((err = exclusive_scan_u32(s_cnt0.as<uint32_t>(), off_first, (uint64_t)nb + 1, scan_sc, s))) return err;
+      k_scatter<<<(unsigned)((n_ent + 255) / 256), 256, 0, s>>>(s_k0.as<uint32_t>(), s_v0.as<uint32_t>(), n_ent, n, (uint32_t)pl.nwin, (uint32_t)pl.nbm,
+                                                               (uint32_t)pl.pf, shared, off_first, s_k1.as<uint32_t>(), s_v1.as<uint32_t>()); B200_LAUNCHED(1);
+      B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
+      sorted_k = s_k1.as<uint32_t>();
+      sorted_v = s_v1.as<uint32_t>();
+      n_live = off_first + nb;
+      acc_sentinel = 0xffffffffu; // zero digits never enter the list
+      prof.mark("sort");
     }
-    prof.mark("sort");
     // K8
     B200_CUDA_TRY(cudaMemsetAsync(bkt, 0, n_buckets * XW * 4, s), B200_UNKNOWN_ERROR);
     uint64_t n_slices;
     if (levels == 0) {
       n_slices = (n_ent + slice - 1) / slice;
       k_accumulate<F, false><<<(unsigned)((n_slices + MSM_THREADS - 1) / MSM_THREADS), MSM_THREADS, 0, s>>>(
-        dk.Current(), dv.Current(), n_ent, nullptr, slice, sentinel, pts, bkt, s_pkey.as<uint32_t>(),
+        sorted_k, sorted_v, n_ent, n_live, slice, acc_sentinel, pts, bkt, s_pkey.as<uint32_t>(),
         s_pflag.as<uint32_t>(), s_ppt.as<uint32_t>(), n_slices, pts_wide); B200_LAUNCHED(1);
       B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     } else {
-      const uint32_t nb = (uint32_t)n_buckets;
       const unsigned gb = (nb + 1 + 255) / 256;
-      k_bounds<<<gb, 256, 0, s>>>(dk.Current(), (uint32_t)n_ent, nb, s_off[0].as<uint32_t>()); B200_LAUNCHED(1);
       uint64_t capl = n_ent; // upper bound of the current level's length (the exact length lives in off[nb] on the device)
-      const uint32_t *lk = dk.Current(), *lp = pts;
+      const uint32_t *lk = sorted_k, *lp = pts;
       uint64_t lcap = 0;     // plane stride of the current (planar) level buffer
       uint4* pbuf = s_pbuf.as<uint4>();
       const uint64_t pcap = cap[0] / 2 + 1;
@@ -636,7 +716,7 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
         uint32_t* off_c = s_off[l & 1].as<uint32_t>();
         uint32_t* off_n = s_off[(l + 1) & 1].as<uint32_t>();
         k_pair_counts<<<gb, 256, 0, s>>>(off_c, nb, s_cnt.as<uint32_t>()); B200_LAUNCHED(1);
-        B200_CUDA_TRY(cub::DeviceScan::ExclusiveSum(s_scan.p, scan_bytes, s_cnt.as<uint32_t>(), off_n, (int)(nb + 1), s), B200_UNKNOWN_ERROR);
+        if ((err = exclusive_scan_u32(s_cnt.as<uint32_t>(), off_n, (uint64_t)nb + 1, scan_sc, s))) return err;
         const uint64_t nq = (capl + 1) / 2;
         const unsigned gp = (unsigned)((nq + (uint64_t)PAIR_J * PAIR_THREADS - 1) / ((uint64_t)PAIR_J * PAIR_THREADS));
         const uint32_t nthr = gp * PAIR_THREADS;
@@ -647,7 +727,7 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
         const uint64_t ocap = cap[(l & 1) + 1];
         const bool last = (l + 1 == levels);
         if (l == 0) {
-          PairSrc<F, true> src = {lk, dv.Current(), lp, 0, pts_wide};
+          PairSrc<F, true> src = {lk, sorted_v, lp, 0, pts_wide};
           k_pair_prefix<F, true><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, nb, PAIR_J, pbuf, pcap, tree);
         } else {
           PairSrc<F, false> src = {lk, nullptr, lp, lcap, false};
@@ -676,7 +756,7 @@ int msm_core(const void* d_scal, const uint32_t* pts_m, uint32_t n, const MsmPla
           }
         }
         if (l == 0) {
-          PairSrc<F, true> src = {lk, dv.Current(), lp, 0, pts_wide};
+          PairSrc<F, true> src = {lk, sorted_v, lp, 0, pts_wide};
           if (last) k_pair_apply<F, true, false><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, off_n, nb, PAIR_J, pbuf, pcap, tree, out_p, ocap, out_k);
           else k_pair_apply<F, true, true><<<gp, PAIR_THREADS, 0, s>>>(src, off_c, off_n, nb, PAIR_J, pbuf, pcap, tree, out_p, ocap, out_k);
         } else {

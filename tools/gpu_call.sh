@@ -1,4 +1,4 @@
 # GPU-box scratch runner used during development (gpurun -- 'bash tools/gpu_call.sh'): edit per experiment.
 mkdir -p gpurun_out
-./build/host_copy_probe > gpurun_out/host_copy_probe.txt 2>&1; cat gpurun_out/host_copy_probe.txt
-timeout 1200 python -m pytest tests/test_gpu_golden.py tests/test_gpu_multi.py tests/test_gpu_ntt.py tests/test_gpu_vec_ops.py -x -q 2>&1 | tail -15 > gpurun_out/t_new.log; cat gpurun_out/t_new.log
+timeout 900 python -m pytest tests/test_gpu_msm.py -x -q -k "bn254 or linearity or pipelined or reference" 2>&1 | tail -8 > gpurun_out/t_sort.log; cat gpurun_out/t_sort.log
+(for lg in 20 22 24 26; do python tools/stage_profile.py $lg 0; B200_MSM_SORT=1 python tools/stage_profile.py $lg 0; done) 2>&1 | grep "^msm" | tee gpurun_out/sort_stage.txt
