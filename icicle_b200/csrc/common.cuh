@@ -30,7 +30,7 @@ static inline int map_alloc_error(cudaError_t e) { return e == cudaErrorMemoryAl
 // b200_set_tuning(); the hot path never calls getenv().  -1 = unset (use the built-in policy).
 enum Tune : int {
   T_MSM_PAIR_LEVELS = 0, T_MSM_CHUNK_TARGET, T_MSM_NO_WIDE_LOADS, T_MSM_PIPELINE_MIN, T_MSM_PIPELINE_CHUNKS, T_MSM_NO_PIPELINE,
-  T_MSM_STAGING_MB, T_MSM_SORT, T_NTT_GEOM, T_NTT31_OFF, T_NTT_COLUMNS_STRIDED, T_NTT_MAXR, T_NTT_TILES, T_NTT_MAXS, T_NTT31_TWO_PASS, T_COPIER_THREADS,
+  T_MSM_STAGING_MB, T_MSM_SORT, T_NTT_GEOM, T_NTT31_OFF, T_NTT_COLUMNS_STRIDED, T_NTT_MAXR, T_NTT_TILES, T_NTT_MAXS, T_NTT31_TMA_OFF, T_COPIER_THREADS,
   T_COUNT
 };
 int tune(Tune k);

@@ -411,7 +411,7 @@ struct RoundDispatch<F, LOGE, 0> {
 };
 
 template <class F, int LOGE, int LOGT>
-__global__ void __launch_bounds__(1 << LOGT, (LOGT >= 9 ? 1 : (LOGT == 8 ? 2 : (LOGT == 7 ? 4 : 8))))
+__global__ void __launch_bounds__(1 << LOGT, (LOGT >= 9 ? 1 : (LOGT == 8 ? ((LOGE <= 2 && F::N <= 8) ? 3 : 2) : (LOGT == 7 ? 4 : 8))))
 k_ntt_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassParams p, uint32_t S, uint64_t total_cols)
 {
   constexpr int E = 1 << LOGE;
@@ -528,7 +528,9 @@ k_ntt_tile(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassPar
 // tile geometry per field width: elements per thread (2^LOGE) and threads per CTA (2^LOGT)
 template <class F>
 struct TileCfg {
-  static constexpr int LOGE = (F::N == 1) ? 5 : (F::N >= 12 ? 2 : 3);
+  // 8-limb fields: 4 elements / thread (radix-4 rounds) fit 85 registers -> 3 CTAs per SM, +10 % over 8 elements / thread at 2 CTAs
+  // (profiles/r2_ntt_tma_and_geometry.txt: 3.79 vs 4.16 ms at 2^24)
+  static constexpr int LOGE = (F::N == 1) ? 5 : (F::N >= 8 ? 2 : 3);
   static constexpr int LOGT = (F::N == 1) ? 9 : 8;
   static constexpr int TILE_LOG = LOGE + LOGT;
   static constexpr int MAX_S = (F::N == 1) ? 10 : 9; // stages per pass

@@ -109,7 +109,7 @@ __device__ __forceinline__ void ntt31_dif_group(F (&e)[8], uint32_t a, uint32_t 
 
 // DIF round over the whole tile.  LASTR (a == 0): rows r = (b << Q) + j hold frequency k = (rev_Q(j) << (S-Q)) | rev_(S-Q)(b);
 // the inter-pass factor g1^k = T_b' * G^rev_Q(j) with b' = rev(b), G = g1^(2^(S-Q)); warps walk b' so that T advances by g1^8.
-template <class F, int Q, bool LASTR>
+template <class F, int Q, bool LASTR, int PAD>
 __device__ __forceinline__ void ntt31_dif_round(uint32_t* __restrict__ tile, const uint32_t* __restrict__ twsm, uint32_t S, uint32_t a, uint32_t lane,
                                                 uint32_t warp, bool interpass, F g1)
 {
@@ -128,7 +128,7 @@ __device__ __forceinline__ void ntt31_dif_round(uint32_t* __restrict__ tile, con
     const uint32_t base = ((g >> a) << (a + Q)) | blow;
     F e[8];
 #pragma unroll
-    for (int j = 0; j < (1 << Q); j++) e[j].v[0] = tile[(base + ((uint32_t)j << a)) * NTT31_ROWPAD + lane];
+    for (int j = 0; j < (1 << Q); j++) e[j].v[0] = tile[(base + ((uint32_t)j << a)) * PAD + lane];
     ntt31_dif_group<F, Q, LASTR>(e, a, blow, twsm, S);
     if (LASTR && interpass) {
       F pw[1 << Q];
@@ -148,12 +148,12 @@ __device__ __forceinline__ void ntt31_dif_round(uint32_t* __restrict__ tile, con
       T.v[0] = A31<F>::mul(T.v[0], g8.v[0]);
     }
 #pragma unroll
-    for (int j = 0; j < (1 << Q); j++) tile[(base + ((uint32_t)j << a)) * NTT31_ROWPAD + lane] = e[j].v[0];
+    for (int j = 0; j < (1 << Q); j++) tile[(base + ((uint32_t)j << a)) * PAD + lane] = e[j].v[0];
   }
 }
 
 // One round of Q stages over the whole tile.  LAST: apply the inter-pass twiddle (per lane l, per row k) before storing.
-template <class F, int Q, bool LAST, bool FIRST>
+template <class F, int Q, bool LAST, bool FIRST, int PAD>
 __device__ __forceinline__ void ntt31_round(uint32_t* __restrict__ tile, const uint32_t* __restrict__ twsm, uint32_t S, uint32_t a, uint32_t lane,
                                             uint32_t warp, bool interpass, F g1)
 {
@@ -172,7 +172,7 @@ __device__ __forceinline__ void ntt31_round(uint32_t* __restrict__ tile, const u
     const uint32_t base = ((g >> a) << (a + Q)) | blow;
     F e[8];
 #pragma unroll
-    for (int j = 0; j < (1 << Q); j++) e[j].v[0] = tile[(base + ((uint32_t)j << a)) * NTT31_ROWPAD + lane];
+    for (int j = 0; j < (1 << Q); j++) e[j].v[0] = tile[(base + ((uint32_t)j << a)) * PAD + lane];
     ntt31_dit_group<F, Q, FIRST>(e, a, blow, twsm, S);
     if (LAST && interpass) {
       F t = T;
@@ -184,17 +184,65 @@ __device__ __forceinline__ void ntt31_round(uint32_t* __restrict__ tile, const u
       T.v[0] = A31<F>::mul(T.v[0], g8.v[0]);
     }
 #pragma unroll
-    for (int j = 0; j < (1 << Q); j++) tile[(base + ((uint32_t)j << a)) * NTT31_ROWPAD + lane] = e[j].v[0];
+    for (int j = 0; j < (1 << Q); j++) tile[(base + ((uint32_t)j << a)) * PAD + lane] = e[j].v[0];
   }
 }
 
-template <class F>
+// ---- TMA (bulk asynchronous copy) helpers: one 128-byte tile row per cp.async.bulk, completion on an mbarrier (loads) or a
+// bulk group (stores).  SASS: UBLKCP.  The rows of a tile are 2^rsh elements apart in HBM, so each row is its own 1-D bulk copy.
+constexpr int NTT31_TMAPAD = 36; // words per shared-memory row: 144 B keeps every row 16-byte aligned for the bulk copies
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "WAIT_%=:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra DONE_%=;\n"
+    "bra WAIT_%=;\n"
+    "DONE_%=:\n"
+    "}\n" ::"r"(smem_u32(bar)),
+    "r"(parity)
+    : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_and_wait_reads()
+{
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// TMA = true: tile rows staged by bulk copies (row stride NTT31_TMAPAD); TMA = false: the LDG/STS path (row stride 33), kept
+// for buffers that are not 16-byte aligned and as the comparison point (knob ntt31_tma_off = 1 selects it).
+template <class F, bool TMA>
 __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassParams p, uint32_t S)
 {
   static_assert(F::N == 1, "k_ntt31 is the 4-byte-field pass");
-  extern __shared__ uint32_t sm[];
+  constexpr int PAD = TMA ? NTT31_TMAPAD : NTT31_ROWPAD;
+  extern __shared__ __align__(16) uint32_t sm[];
   uint32_t* tile = sm;
-  uint32_t* twsm = sm + ((size_t)NTT31_ROWPAD << S);
+  uint32_t* twsm = sm + ((size_t)PAD << S);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(twsm + ((size_t)1 << (S - 1))); // 8-byte aligned: both terms are even word counts
   constexpr int NW = NTT31_THREADS / 32;
   const uint32_t T = threadIdx.x, lane = T & 31, warp = T >> 5;
   const uint32_t n_log = p.n_log;
@@ -206,7 +254,10 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31(const uint32_t* __re
   const uint64_t colg = col0 + lane;
   const uint64_t hi_part = (colg >> rsh) << n_log; // batch index (the tile never straddles two transforms: rsh >= 5)
   const uint64_t lowfull = colg & rmask;
+  const uint32_t nrows = 1u << S;
+  const bool tma_load = TMA && !p.in_mul;
 
+  if (TMA && T == 0) mbar_init(mbar, 1);
   // ---- twiddle table of the 2^S-point sub-transform ----
   for (uint32_t j = T; j < (1u << (S - 1)); j += NTT31_THREADS) {
     uint64_t ex = (uint64_t)j << (p.dom_log - S);
@@ -214,8 +265,12 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31(const uint32_t* __re
     twsm[j] = load_twiddle<F>(p.tw, ex).v[0];
   }
   // ---- load: row m of the tile goes to shared-memory row rev_S(m) ----
-  {
-    const uint32_t nrows = 1u << S;
+  if (tma_load) {
+    __syncthreads(); // the mbarrier is initialised
+    if (T == 0) mbar_expect_tx(mbar, nrows * 128u);
+    const uint32_t* __restrict__ row0 = src + (((col0 >> rsh) << n_log) | (col0 & rmask)); // column 0 of the tile: 128-byte aligned
+    for (uint32_t m = T; m < nrows; m += NTT31_THREADS) bulk_g2s(tile + (__brev(m) >> (32 - S)) * PAD, row0 + ((uint64_t)m << rsh), 128u, mbar);
+  } else {
     constexpr int LD = 8; // independent 128-byte row loads in flight per warp
     const uint32_t* __restrict__ srow = src + (hi_part | lowfull);
     for (uint32_t m0 = warp; m0 < nrows; m0 += NW * LD) {
@@ -235,7 +290,7 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31(const uint32_t* __re
 #pragma unroll
       for (int u = 0; u < LD; u++) {
         const uint32_t m = m0 + u * NW;
-        if (m < nrows) tile[(__brev(m) >> (32 - S)) * NTT31_ROWPAD + lane] = v[u];
+        if (m < nrows) tile[(__brev(m) >> (32 - S)) * PAD + lane] = v[u];
       }
     }
   }
@@ -248,6 +303,7 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31(const uint32_t* __re
     if (p.inverse) ex = (0 - ex) & dom_mask;
     g1 = load_twiddle<F>(p.tw, ex);
   }
+  if (tma_load) mbar_wait(mbar, 0);
   __syncthreads();
 
   // ---- rounds of <= 3 DIT stages ----
@@ -256,13 +312,13 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31(const uint32_t* __re
     const uint32_t q = (S - a >= 3) ? 3 : (S - a);
     const bool last = (a + q == S);
     if (last) { // S >= 5: the last round is never the first
-      if (q == 3) ntt31_round<F, 3, true, false>(tile, twsm, S, a, lane, warp, interpass, g1);
-      else if (q == 2) ntt31_round<F, 2, true, false>(tile, twsm, S, a, lane, warp, interpass, g1);
-      else ntt31_round<F, 1, true, false>(tile, twsm, S, a, lane, warp, interpass, g1);
+      if (q == 3) ntt31_round<F, 3, true, false, PAD>(tile, twsm, S, a, lane, warp, interpass, g1);
+      else if (q == 2) ntt31_round<F, 2, true, false, PAD>(tile, twsm, S, a, lane, warp, interpass, g1);
+      else ntt31_round<F, 1, true, false, PAD>(tile, twsm, S, a, lane, warp, interpass, g1);
     } else if (a == 0) {
-      ntt31_round<F, 3, false, true>(tile, twsm, S, a, lane, warp, false, g1);
+      ntt31_round<F, 3, false, true, PAD>(tile, twsm, S, a, lane, warp, false, g1);
     } else {
-      ntt31_round<F, 3, false, false>(tile, twsm, S, a, lane, warp, false, g1);
+      ntt31_round<F, 3, false, false, PAD>(tile, twsm, S, a, lane, warp, false, g1);
     }
     a += q;
     __syncthreads();
@@ -270,36 +326,60 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31(const uint32_t* __re
 
   // ---- store in the autosort layout: idx = batch | (untransformed << (S+done)) | (k << done) | (transformed so far) ----
   const uint32_t done = p.done;
-  const uint32_t nrows = 1u << S;
   F scale = F::one();
   const bool has_scale = p.last && !p.out_mul && p.out_scale;
   if (has_scale) scale.v[0] = p.out_scale[0];
   if (done == 0) {
-    // first pass: column c of the tile is the contiguous run [(lowfull0 + c) << S, +2^S) -> lane = frequency
+    // first pass: column c of the tile is the contiguous run [(lowfull0 + c) << S, +2^S) -> lanes walk the frequency k
     const uint64_t base0 = ((col0 >> rsh) << n_log) | ((col0 & rmask) << S);
-    uint32_t* __restrict__ drow = dst + base0 + lane;
-    const uint32_t ntask = 32u * (nrows >> 5);
-    for (uint32_t task = warp; task < ntask; task += NW) {
-      const uint32_t c = task & 31, k = ((task >> 5) << 5) | lane;
-      const uint32_t off = (c << S) + ((task >> 5) << 5);
-      uint32_t v = tile[k * NTT31_ROWPAD + c];
-      if (p.last) {
-        if (p.out_mul) v = A31<F>::mul(v, p.out_mul[(base0 + off + lane) & ntt_mask]);
-        else if (has_scale) v = A31<F>::mul(v, scale.v[0]);
+    if constexpr (TMA) {
+      // a warp stores 4 columns x 8 consecutive frequencies (four full 32-byte sectors); with the 36-word row stride the 32 reads
+      // hit 32 different banks: bank = (4k + c) mod 32 with k mod 8 = lane & 7 and c = 4*cq + (lane >> 3)
+      const uint32_t ntask = 8u * (nrows >> 3);
+      for (uint32_t task = warp; task < ntask; task += NW) {
+        const uint32_t c = ((task & 7) << 2) | (lane >> 3), k = ((task >> 3) << 3) | (lane & 7);
+        const uint64_t idx = base0 + ((uint64_t)c << S) + k;
+        uint32_t v = tile[k * PAD + c];
+        if (p.last) {
+          if (p.out_mul) v = A31<F>::mul(v, p.out_mul[idx & ntt_mask]);
+          else if (has_scale) v = A31<F>::mul(v, scale.v[0]);
+        }
+        dst[idx] = v;
       }
-      drow[off] = v;
+    } else {
+      uint32_t* __restrict__ drow = dst + base0 + lane;
+      const uint32_t ntask = 32u * (nrows >> 5);
+      for (uint32_t task = warp; task < ntask; task += NW) {
+        const uint32_t c = task & 31, k = ((task >> 5) << 5) | lane;
+        const uint32_t off = (c << S) + ((task >> 5) << 5);
+        uint32_t v = tile[k * PAD + c];
+        if (p.last) {
+          if (p.out_mul) v = A31<F>::mul(v, p.out_mul[(base0 + off + lane) & ntt_mask]);
+          else if (has_scale) v = A31<F>::mul(v, scale.v[0]);
+        }
+        drow[off] = v;
+      }
     }
   } else {
-    // later passes (done >= 5): the 32 columns of a row stay adjacent -> lane = column
-    const uint64_t base1 = hi_part | ((lowfull >> done) << (S + done)) | (lowfull & ((1ull << done) - 1));
-    uint32_t* __restrict__ drow = dst + base1;
-    for (uint32_t k = warp; k < nrows; k += NW) {
-      uint32_t v = tile[k * NTT31_ROWPAD + lane];
-      if (p.last) {
-        if (p.out_mul) v = A31<F>::mul(v, p.out_mul[(base1 | ((uint64_t)k << done)) & ntt_mask]);
-        else if (has_scale) v = A31<F>::mul(v, scale.v[0]);
+    // later passes (done >= 5): the 32 columns of a row stay adjacent -> one 128-byte run per row
+    const uint64_t lowfull0 = col0 & rmask;
+    const uint64_t base1_0 = ((col0 >> rsh) << n_log) | ((lowfull0 >> done) << (S + done)) | (lowfull0 & ((1ull << done) - 1));
+    const bool plain = !(p.last && (p.out_mul || has_scale));
+    if (TMA && plain) {
+      fence_async_proxy(); // the rounds' generic-proxy writes must be visible to the bulk copies
+      __syncthreads();
+      for (uint32_t k = T; k < nrows; k += NTT31_THREADS) bulk_s2g(dst + base1_0 + ((uint64_t)k << done), tile + k * PAD, 128u);
+      bulk_commit_and_wait_reads(); // shared memory must stay alive until the copies have read it
+    } else {
+      uint32_t* __restrict__ drow = dst + base1_0 + lane;
+      for (uint32_t k = warp; k < nrows; k += NW) {
+        uint32_t v = tile[k * PAD + lane];
+        if (p.last) {
+          if (p.out_mul) v = A31<F>::mul(v, p.out_mul[((base1_0 + lane) | ((uint64_t)k << done)) & ntt_mask]);
+          else if (has_scale) v = A31<F>::mul(v, scale.v[0]);
+        }
+        drow[(uint64_t)k << done] = v;
       }
-      drow[k << done] = v;
     }
   }
 }
@@ -307,13 +387,16 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31(const uint32_t* __re
 // In-place schedule (output bit-reversed: kNR / kNM, ntt.cu): the pass transforms the digit at bits [lo, lo+S) where it
 // lies.  lo >= 5: the 32 tile columns are the 32 lowest position bits (lane = column).  lo == 0 (the last pass): the tile is one
 // contiguous run of 32 * 2^S elements (lane = row).  Natural rows + DIF rounds leave frequency k at row rev_S(k), as the schedule wants.
-template <class F>
+// TMA = true (passes with lo >= 5 only, no input multiplier): rows staged in and out by bulk copies, row stride NTT31_TMAPAD.
+template <class F, bool TMA>
 __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31_inplace(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, PassParams p, uint32_t S)
 {
   static_assert(F::N == 1, "k_ntt31_inplace is the 4-byte-field pass");
-  extern __shared__ uint32_t sm[];
+  constexpr int PAD = TMA ? NTT31_TMAPAD : NTT31_ROWPAD;
+  extern __shared__ __align__(16) uint32_t sm[];
   uint32_t* tile = sm;
-  uint32_t* twsm = sm + ((size_t)NTT31_ROWPAD << S);
+  uint32_t* twsm = sm + ((size_t)PAD << S);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(twsm + ((size_t)1 << (S - 1)));
   constexpr int NW = NTT31_THREADS / 32;
   const uint32_t T = threadIdx.x, lane = T & 31, warp = T >> 5;
   const uint32_t n_log = p.n_log, lo = p.lo;
@@ -333,7 +416,13 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31_inplace(const uint32
     twsm[j] = load_twiddle<F>(p.tw, ex).v[0];
   }
   constexpr int LD = 8;
-  if (by_col) {
+  if constexpr (TMA) { // by_col, no in_mul (launch_ntt31): row m = 128 contiguous bytes at col_base(lane 0) + (m << lo)
+    if (T == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (T == 0) mbar_expect_tx(mbar, nrows * 128u);
+    const uint64_t cb0 = ((col0 >> lo) << (lo + S)) | (col0 & lomask);
+    for (uint32_t m = T; m < nrows; m += NTT31_THREADS) bulk_g2s(tile + m * PAD, src + cb0 + ((uint64_t)m << lo), 128u, mbar);
+  } else if (by_col) {
     for (uint32_t m0 = warp; m0 < nrows; m0 += NW * LD) {
       uint32_t v[LD];
 #pragma unroll
@@ -351,7 +440,7 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31_inplace(const uint32
 #pragma unroll
       for (int u = 0; u < LD; u++) {
         const uint32_t m = m0 + u * NW;
-        if (m < nrows) tile[m * NTT31_ROWPAD + lane] = v[u];
+        if (m < nrows) tile[m * PAD + lane] = v[u];
       }
     }
   } else {
@@ -370,7 +459,7 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31_inplace(const uint32
       for (int u = 0; u < LD; u++) {
         const uint32_t task = t0 + u * NW;
         const uint32_t c = task & 31, m = ((task >> 5) << 5) | lane;
-        if (task < ntask) tile[m * NTT31_ROWPAD + c] = v[u];
+        if (task < ntask) tile[m * PAD + c] = v[u];
       }
     }
   }
@@ -382,6 +471,7 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31_inplace(const uint32
     if (p.inverse) ex = (0 - ex) & dom_mask;
     g1 = load_twiddle<F>(p.tw, ex);
   }
+  if constexpr (TMA) mbar_wait(mbar, 0);
   __syncthreads();
 
   // ---- DIF rounds, top stages first; the last round covers stages [0, q0) with q0 = S mod 3 (or 3) ----
@@ -390,12 +480,12 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31_inplace(const uint32
     uint32_t a = S;
     while (a > q0) {
       a -= 3;
-      ntt31_dif_round<F, 3, false>(tile, twsm, S, a, lane, warp, false, g1);
+      ntt31_dif_round<F, 3, false, PAD>(tile, twsm, S, a, lane, warp, false, g1);
       __syncthreads();
     }
-    if (q0 == 3) ntt31_dif_round<F, 3, true>(tile, twsm, S, 0, lane, warp, interpass, g1);
-    else if (q0 == 2) ntt31_dif_round<F, 2, true>(tile, twsm, S, 0, lane, warp, interpass, g1);
-    else ntt31_dif_round<F, 1, true>(tile, twsm, S, 0, lane, warp, interpass, g1);
+    if (q0 == 3) ntt31_dif_round<F, 3, true, PAD>(tile, twsm, S, 0, lane, warp, interpass, g1);
+    else if (q0 == 2) ntt31_dif_round<F, 2, true, PAD>(tile, twsm, S, 0, lane, warp, interpass, g1);
+    else ntt31_dif_round<F, 1, true, PAD>(tile, twsm, S, 0, lane, warp, interpass, g1);
     __syncthreads();
   }
 
@@ -403,10 +493,16 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31_inplace(const uint32
   F scale = F::one();
   const bool has_scale = p.last && !p.out_mul && p.out_scale;
   if (has_scale) scale.v[0] = p.out_scale[0];
-  if (by_col) {
+  if constexpr (TMA) { // never the last pass (lo >= 5): plain rows out
+    const uint64_t cb0 = ((col0 >> lo) << (lo + S)) | (col0 & lomask);
+    fence_async_proxy();
+    __syncthreads();
+    for (uint32_t m = T; m < nrows; m += NTT31_THREADS) bulk_s2g(dst + cb0 + ((uint64_t)m << lo), tile + m * PAD, 128u);
+    bulk_commit_and_wait_reads();
+  } else if (by_col) {
     for (uint32_t m = warp; m < nrows; m += NW) {
       const uint64_t pos = col_base + (m << lo);
-      uint32_t v = tile[m * NTT31_ROWPAD + lane];
+      uint32_t v = tile[m * PAD + lane];
       if (p.last) {
         if (p.out_mul) v = A31<F>::mul(v, p.out_mul[__brevll(pos & ntt_mask) >> rev_shift]);
         else if (has_scale) v = A31<F>::mul(v, scale.v[0]);
@@ -418,7 +514,7 @@ __global__ void __launch_bounds__(NTT31_THREADS, 3) k_ntt31_inplace(const uint32
     for (uint32_t task = warp; task < ntask; task += NW) {
       const uint32_t c = task & 31, m = ((task >> 5) << 5) | lane;
       const uint64_t pos = ((col0 + c) << S) | m;
-      uint32_t v = tile[m * NTT31_ROWPAD + c];
+      uint32_t v = tile[m * PAD + c];
       if (p.last) {
         if (p.out_mul) v = A31<F>::mul(v, p.out_mul[__brevll(pos & ntt_mask) >> rev_shift]);
         else if (has_scale) v = A31<F>::mul(v, scale.v[0]);
@@ -437,11 +533,26 @@ int launch_ntt31(const uint32_t* src, uint32_t* dst, const PassParams& p, int S,
     const uint64_t blocks = total_cols / 32; // n_log - S >= 5: always a whole number of 32-column tiles
     const size_t smem = (((size_t)NTT31_ROWPAD << S) + ((size_t)1 << (S - 1))) * 4;
     if (p.rot) {
-      B200_CUDA_TRY(cudaFuncSetAttribute(k_ntt31<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), B200_UNKNOWN_ERROR);
-      k_ntt31<F><<<(unsigned)blocks, NTT31_THREADS, smem, s>>>(src, dst, p, (uint32_t)S); B200_LAUNCHED(1);
+      // bulk-copy (TMA) staging needs 16-byte aligned rows: guaranteed for cudaMalloc'd / staged buffers, checked for the rest
+      const bool tma = tune(T_NTT31_TMA_OFF) <= 0 && ((((uintptr_t)src) | ((uintptr_t)dst)) & 15u) == 0;
+      if (tma) {
+        const size_t smem_t = (((size_t)NTT31_TMAPAD << S) + ((size_t)1 << (S - 1))) * 4 + 16;
+        B200_CUDA_TRY(cudaFuncSetAttribute(k_ntt31<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t), B200_UNKNOWN_ERROR);
+        k_ntt31<F, true><<<(unsigned)blocks, NTT31_THREADS, smem_t, s>>>(src, dst, p, (uint32_t)S); B200_LAUNCHED(1);
+      } else {
+        B200_CUDA_TRY(cudaFuncSetAttribute(k_ntt31<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), B200_UNKNOWN_ERROR);
+        k_ntt31<F, false><<<(unsigned)blocks, NTT31_THREADS, smem, s>>>(src, dst, p, (uint32_t)S); B200_LAUNCHED(1);
+      }
     } else {
-      B200_CUDA_TRY(cudaFuncSetAttribute(k_ntt31_inplace<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), B200_UNKNOWN_ERROR);
-      k_ntt31_inplace<F><<<(unsigned)blocks, NTT31_THREADS, smem, s>>>(src, dst, p, (uint32_t)S); B200_LAUNCHED(1);
+      const bool tma = tune(T_NTT31_TMA_OFF) <= 0 && ((((uintptr_t)src) | ((uintptr_t)dst)) & 15u) == 0 && p.lo >= 5 && !p.in_mul;
+      if (tma) {
+        const size_t smem_t = (((size_t)NTT31_TMAPAD << S) + ((size_t)1 << (S - 1))) * 4 + 16;
+        B200_CUDA_TRY(cudaFuncSetAttribute(k_ntt31_inplace<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t), B200_UNKNOWN_ERROR);
+        k_ntt31_inplace<F, true><<<(unsigned)blocks, NTT31_THREADS, smem_t, s>>>(src, dst, p, (uint32_t)S); B200_LAUNCHED(1);
+      } else {
+        B200_CUDA_TRY(cudaFuncSetAttribute(k_ntt31_inplace<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), B200_UNKNOWN_ERROR);
+        k_ntt31_inplace<F, false><<<(unsigned)blocks, NTT31_THREADS, smem, s>>>(src, dst, p, (uint32_t)S); B200_LAUNCHED(1);
+      }
     }
     B200_CUDA_TRY(cudaGetLastError(), B200_UNKNOWN_ERROR);
     return B200_SUCCESS;

@@ -25,7 +25,7 @@ namespace {
   // ---- tuning knobs: B200_<NAME> read once at load; b200_set_tuning() afterwards ------------------------------------------
   const char* const kTuneNames[b200::T_COUNT] = {
     "msm_pair_levels", "msm_chunk_target", "msm_no_wide_loads", "msm_pipeline_min", "msm_pipeline_chunks", "msm_no_pipeline",
-    "msm_staging_mb", "msm_sort", "ntt_geom", "ntt31_off", "ntt_columns_strided", "ntt_maxr", "ntt_tiles", "ntt_maxs", "ntt31_two_pass", "copier_threads"};
+    "msm_staging_mb", "msm_sort", "ntt_geom", "ntt31_off", "ntt_columns_strided", "ntt_maxr", "ntt_tiles", "ntt_maxs", "ntt31_tma_off", "copier_threads"};
   std::atomic<int> g_tune[b200::T_COUNT];
   struct TuneInit {
     TuneInit()
