@@ -42,13 +42,14 @@ ALG_BYTES_PER_POINT = 96  # |scalar_t| + |affine_t| for BN254 G1
 ALG_BYTES_PER_NTT_ELEM = 64  # one read + one write of a 32-byte element
 IMAD_WIDE_PEAK = 9.26e12  # measured on this pool's B200 (tools/imad_bench.cu, profiles/r1_imad_microbench.txt): IMAD.WIDE.U32.X thread-instr/s
 # dram__bytes_read.sum + dram__bytes_write.sum of the bucket-accumulation stage of ONE MSM at the headline config (2^26 points,
-# c = 20, 5 pair levels): all k_pair_prefix / k_pair_apply / k_inv_* launches + k_accumulate, from the ncu launch list
-# profiles/r1_ncu_launches_msm_2p26.txt (218.4 GB read + 89.4 GB write).  It is ~48x the algorithmic 6.44 GB: level 0 gathers
-# every point once per window in each of its two passes and every level writes its halved list (planar scratch); the stage is
-# bound by the random-sector rate of HBM at level 0 and by IMAD.WIDE issue above it, not by bytes.
-NCU_TRAFFIC_BYTES = {(26, 20): 307.8e9}
+# c = 20, 5 pair levels): all k_pair_prefix / k_pair_apply / k_inv_* / scan launches + k_accumulate, from the ncu launch list
+# profiles/r2_ncu_launches_msm_2p26.txt.  It is ~70x the algorithmic 6.44 GB: level 0 gathers every point once per window in each
+# of its two passes -- and since round 2 no longer lowers the device-wide L2 fetch granularity behind the caller's back, every
+# random 32-byte gather pulls a 128-byte line (round 1 with the limit at 32 B: 307.8 GB, same run time) -- and every level writes
+# its halved list (planar scratch); the stage is bound by the random-sector rate of HBM at level 0 and by IMAD.WIDE issue above it.
+NCU_TRAFFIC_BYTES = {(26, 20): 446.8e9}  # round 2 (profiles/r2_ncu_launches_msm_2p26.txt); 307.8e9 with the opt-in l2_fetch_granularity = 32
 # dram bytes of ONE forward BN254 NTT of 2^24 (3 k_ntt_tile passes), from profiles/; algorithmic = 1.07 GB
-NCU_NTT_TRAFFIC_BYTES = {24: 3.60e9}
+NCU_NTT_TRAFFIC_BYTES = {24: 4.02e9}  # 3 passes: 1.46 + 0.54 + 0.54 GB read, 3 x 0.49 GB written (profiles/r2_ncu_launches_ntt_bn254_2p24.txt)
 CPU_NOTE = "icicle CPU backend (oracle/_ref built from /root/reference sources with g++ -O3; Taskflow STAND-IN thread pool, not upstream's clang + Taskflow 3.8; auto window size)"
 
 
@@ -479,7 +480,7 @@ def run_ntt_secondary(torch, ib, common, args, dev, peak, scalars, ref, have_fro
     a = ALG_BYTES_PER_NTT_ELEM * nn / (out["forward"]["ms"] * 1e-3) / 1e9
     ntt = {"metric": "bn254_ntt_elements_per_s", "logn": nl, "ordering": "kNN", **out,
            "roofline": {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": NCU_NTT_TRAFFIC_BYTES.get(nl),
-                        "kernel": "k_ntt_tile<Fp<bn254_fr>> passes (IMAD.WIDE bound)"}}
+                        "kernel": "k_ntt_tile<Fp<bn254_fr>, 2, 8> x 3 passes (radix-4 rounds, 3 CTAs/SM; IMAD.WIDE bound)"}}
     # e2e: host vectors in and out through the plugin call (H2D + D2H of 32 B/element each way inside the timed region)
     hx = ib.to_host(x)
     hy = np.zeros_like(hx)   # caller-owned output vector, already touched (first-touch page faults are not the backend's)

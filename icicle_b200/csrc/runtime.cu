@@ -139,6 +139,14 @@ int b200_get_last_profile(char* names_out, int names_cap, float* ms_out, int max
 int b200_set_tuning(const char* name, int value)
 {
   if (!name) return B200_INVALID_POINTER;
+  if (!strcmp(name, "l2_fetch_granularity")) {
+    // OPT-IN device-wide setting (round 1 applied it silently): cudaLimitMaxL2FetchGranularity of the CURRENT device.  32 makes the
+    // MSM's random 32-byte point gathers fetch one sector instead of a whole 128-byte line from HBM (bucket-accumulation DRAM
+    // traffic 447 -> 308 GB per 2^26 MSM, same run time: the level is bound by the sector rate, profiles/r2_ncu_launches_msm_2p26.txt)
+    if (value != 32 && value != 64 && value != 128) return B200_INVALID_ARGUMENT;
+    B200_CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value), B200_UNKNOWN_ERROR);
+    return B200_SUCCESS;
+  }
   for (int i = 0; i < b200::T_COUNT; i++) {
     if (!strcmp(name, kTuneNames[i])) {
       g_tune[i].store(value < 0 ? -1 : value);
