@@ -50,7 +50,16 @@ IMAD_WIDE_PEAK = 9.26e12  # measured on this pool's B200 (tools/imad_bench.cu, p
 NCU_TRAFFIC_BYTES = {(26, 20): 446.8e9}  # round 2 (profiles/r2_ncu_launches_msm_2p26.txt); 307.8e9 with the opt-in l2_fetch_granularity = 32
 # dram bytes of ONE forward BN254 NTT of 2^24 (3 k_ntt_tile passes), from profiles/; algorithmic = 1.07 GB
 NCU_NTT_TRAFFIC_BYTES = {24: 4.02e9}  # 3 passes: 1.46 + 0.54 + 0.54 GB read, 3 x 0.49 GB written (profiles/r2_ncu_launches_ntt_bn254_2p24.txt)
-CPU_NOTE = "icicle CPU backend (oracle/_ref built from /root/reference sources with g++ -O3; Taskflow STAND-IN thread pool, not upstream's clang + Taskflow 3.8; auto window size)"
+CPU_NOTE = "icicle CPU backend (oracle/_ref built from /root/reference sources with g++ -O3; Taskflow STAND-IN thread pool, not upstream's clang + Taskflow 3.8; auto window size; `cpu_quota` = CPUs the container's cgroup grants, the reference starts `cores` threads regardless)"
+
+
+def cpu_quota():
+    """CPUs the container really grants (cgroup v2 cpu.max); the GPU boxes of this pool show 128 cores under a 16-CPU quota."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if q == "max" else round(int(q) / int(per), 2)
+    except Exception:
+        return None
 
 
 def hbm_peak():
@@ -187,7 +196,7 @@ def run_reference_arm(args, rank, out_fd):
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (254-bit modular integers)",
         "data": "synthetic (reference generators: uniform scalars, 100 distinct points repeated)",
         "config": {"workload": f"BN254 G1 MSM 2^{args.logn} (bounded sample: 2^{sample_log} points per step on the host cores)"},
-        "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "reference",
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "cpu_quota": cpu_quota(), "kind": "reference",
                          "sample": f"{CPU_NOTE}; MSM of 2^{sample_log} points, mean of {args.steps}; per-step times {[round(x, 3) for x in ts]} s"},
         "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -215,7 +224,7 @@ def cpu_baseline_and_parity(ib, ref, budget_s=20.0):
     t = min(t1, t2)
     got = ib.msm(ib.Curve.BN254_G1, s, P, n)
     ok = bool(ref.projective_eq(got[0], exp[0]))
-    cpu = {"value": n / t, "unit": "points/s", "cores": os.cpu_count(), "kind": "reference",
+    cpu = {"value": n / t, "unit": "points/s", "cores": os.cpu_count(), "cpu_quota": cpu_quota(), "kind": "reference",
            "sample": f"{CPU_NOTE}; BN254 G1 MSM 2^{target} points (seeded scalars, 2^14 distinct points tiled), best of 2 ({t1:.2f} s, {t2:.2f} s)"}
     return cpu, {"what": "GPU (host-pointer path) == reference CPU backend on identical bytes, projective_eq", "logn": target, "ok": ok}
 
@@ -523,7 +532,7 @@ def run_ntt_secondary(torch, ib, common, args, dev, peak, scalars, ref, have_fro
         got = ib.ntt(F, hs, sn, ib.NTTDir.kForward)
         back = ib.ntt(F, exp, sn, ib.NTTDir.kInverse)
         ref.ntt_release_domain()
-        ntt["cpu_baseline"] = {"value": sn / min(ts), "unit": "elements/s", "cores": os.cpu_count(), "kind": "reference",
+        ntt["cpu_baseline"] = {"value": sn / min(ts), "unit": "elements/s", "cores": os.cpu_count(), "cpu_quota": cpu_quota(), "kind": "reference",
                                "sample": f"{CPU_NOTE}; BN254 forward NTT 2^{sl}, best of 3 ({min(ts):.3f} s)"}
         ntt["parity_checked"] = {"what": "GPU forward NTT == reference CPU backend (memcmp) and GPU inverse of the reference output == input", "logn": sl,
                                  "ok": bool(np.array_equal(got, exp) and np.array_equal(back, hs))}

@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <thread>
@@ -22,11 +24,39 @@ namespace b200 {
 
 int tune_copier_threads(); // common.cuh: tune(T_COPIER_THREADS)
 // host threads moving pageable memory through the pinned ring: enough to keep PCIe (~55 GB/s) busy with ~6-8 GB/s memcpys each
+// CPUs this process may really use: the cgroup v2 quota (containers often show every core of the box but grant a fraction:
+// the GPU boxes of this pool expose 128 cores with cpu.max = 16 CPUs), else the affinity mask / core count
+inline int usable_cpus()
+{
+  static const int cached = [] {
+    int n = (int)std::thread::hardware_concurrency();
+    if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+      long long quota = 0, period = 0;
+      char first[32] = {0};
+      if (fscanf(f, "%31s %lld", first, &period) == 2 && strcmp(first, "max") != 0 && period > 0) {
+        quota = atoll(first);
+        if (quota > 0) n = (int)std::max<long long>(1, std::min<long long>(n, quota / period));
+      }
+      fclose(f);
+    }
+    return n > 0 ? n : 8;
+  }();
+  return cached;
+}
+// host threads moving pageable memory through the pinned ring: enough to keep PCIe (~55 GB/s) busy with ~8-12 GB/s memcpys each
+// (8 is the measured optimum on the 128-core / 16-CPU-quota box, profiles/r2_e2e_copier_threads.txt), but never more than this
+// rank's share of the CPUs the container grants (one process per GPU: LOCAL_WORLD_SIZE ranks share them)
 inline int copier_thread_count()
 {
   const int forced = tune_copier_threads();
   if (forced > 0) return std::min(forced, 32);
-  return (int)std::min<size_t>(8, std::max<unsigned>(2, std::thread::hardware_concurrency() / 8)); // 8 measured best on the 128-core box (profiles/r2_e2e_copier_threads.txt)
+  static const int ranks = [] {
+    const char* e = getenv("LOCAL_WORLD_SIZE"); // read once per process, not on the hot path
+    const int r = e ? atoi(e) : 1;
+    return r > 0 ? r : 1;
+  }();
+  const int share = usable_cpus() / ranks - 2; // leave room for the launching thread and the caller's own work
+  return std::max(2, std::min(8, share));
 }
 
 struct CopierCtx {

