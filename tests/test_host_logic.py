@@ -171,3 +171,21 @@ def test_ec_host_emulation_matches_python_ints(tmp_path):
     import check_ec
     n, m, bad = check_ec.run(exe, n_random=40, seed=7)
     assert n == m and not bad, bad[:2]
+
+
+def test_tuning_table_roundtrip():
+    """b200_set_tuning / b200_get_tuning (developer knobs: read once from B200_* at load, never via getenv on the hot path): unknown
+    names are rejected, negative values unset, values survive a round trip; pure host logic."""
+    import icicle_b200 as ib
+    from icicle_b200 import capi
+    old = ib.get_tuning("msm_pair_levels")
+    ib.set_tuning("msm_pair_levels", 3)
+    assert ib.get_tuning("msm_pair_levels") == 3
+    ib.set_tuning("msm_pair_levels", None)
+    assert ib.get_tuning("msm_pair_levels") == -1
+    ib.set_tuning("msm_pair_levels", old)
+    with pytest.raises(ib.IcicleError):
+        ib.set_tuning("no_such_knob", 1)
+    assert capi.lib.b200_get_tuning(b"no_such_knob") == -1
+    for lo, hi in ((0, 10), (3, 8), (10, 3)):
+        assert ib.shard_range(hi, 4, 0)[0] == 0
