@@ -62,6 +62,28 @@ def cpu_quota():
         return None
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """CPU affinity per rank (round-1 verdict item 8): run this process -- and therefore the host vectors it first-touches and the
+    library's copier threads, which inherit the mask -- on the cores of the NUMA node its GPU hangs off
+    (/sys/bus/pci/devices/<bus id>/local_cpulist).  torchrun leaves ranks floating over both sockets; a rank whose pageable
+    vectors live on the other socket reads them over UPI and the e2e number collapses (profiles/r2_e2e_numa.txt)."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        txt = open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return txt
+    except Exception:
+        pass
+    return None
+
+
 def hbm_peak():
     try:
         d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -297,6 +319,7 @@ def _main(out_fd):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (the product has no CPU path)")
+    numa_cpus = None if os.environ.get("B200_BENCH_NO_NUMA_BIND") else bind_to_gpu_numa_node(torch, local_rank)
     torch.cuda.set_device(local_rank)
     ib.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -400,30 +423,30 @@ def _main(out_fd):
             ms = timed(torch, dist, world, dev, one, k2, warmup=1)
             variants[name] = {"value": world * n / (ms * 1e-3), "ms_per_step": ms}
 
-        def cabi_pageable():
-            ib.msm(CURVE, h_s, h_p, n, ib.MSMConfig(c=args.c), h_res)   # host in, host out: blocking call
-        run_variant("cabi_pageable", cabi_pageable)
-        if have_frontend:
-            def frontend_pageable():
-                ref.set_device("CUDA", local_rank)
-                h_res[:] = ref.msm(h_s, h_p, n, c=args.c)
-            run_variant("frontend_pageable", frontend_pageable)
-            ref.set_device("CPU", 0)
         p_s, p1 = pinned_array(ib, (n, 8))
         p_p, p2 = pinned_array(ib, (n, 16))
         p_s[:] = h_s
         p_p[:] = h_p
 
-        def cabi_pinned():
-            ib.msm(CURVE, p_s, p_p, n, ib.MSMConfig(c=args.c), h_res)
-        run_variant("cabi_pinned", cabi_pinned)
+        def frontend(s_arr, p_arr):
+            ref.set_device("CUDA", local_rank)
+            h_res[:] = ref.msm(s_arr, p_arr, n, c=args.c)
+        if have_frontend:
+            run_variant("frontend_pinned", lambda: frontend(p_s, p_p))
+            run_variant("frontend_pageable", lambda: frontend(h_s, h_p))
+            ref.set_device("CPU", 0)
+        run_variant("cabi_pinned", lambda: ib.msm(CURVE, p_s, p_p, n, ib.MSMConfig(c=args.c), h_res))    # host in, host out: blocking call
+        run_variant("cabi_pageable", lambda: ib.msm(CURVE, h_s, h_p, n, ib.MSMConfig(c=args.c), h_res))
         ib.capi.lib.b200_host_free_pinned(p1)
         ib.capi.lib.b200_host_free_pinned(p2)
-        head = "frontend_pageable" if "frontend_pageable" in variants else "cabi_pageable"
+        head = "frontend_pinned" if "frontend_pinned" in variants else "cabi_pinned"
         e2e = {"value": variants[head]["value"], "unit": "points/s", "h2d_bytes_per_step": ALG_BYTES_PER_POINT * n, "d2h_bytes_per_step": 96,
                "ms_per_step": variants[head]["ms_per_step"], "steps": k2, "path": head,
-               "path_note": ("unmodified reference frontend bn254_msm with Device{CUDA} -> dispatcher -> registration shim -> C ABI, pageable host vectors"
-                             if head == "frontend_pageable" else "C ABI b200_msm with pageable host vectors (reference frontend build not present)"),
+               "path_note": ("the PLUGIN call: unmodified reference frontend bn254_msm with Device{CUDA} -> dispatcher -> registration shim -> C ABI, host vectors in "
+                             "PINNED memory (the bench contract); `variants` lists the same call with PAGEABLE vectors (what Rust/Go/C++ callers usually hold: moved "
+                             "through the backend's pinned copier ring) and the bare C-ABI calls.  Pageable vectors are bound by host memory traffic shared by all "
+                             "ranks at N > 1 (profiles/r2_e2e_numa.txt)"
+                             if head == "frontend_pinned" else "C ABI b200_msm with pinned host vectors (reference frontend build not present)"),
                "variants": variants}
         del h_s, h_p, p_s, p_p
 
@@ -453,7 +476,8 @@ def _main(out_fd):
             "dtype": "u32 limbs (254-bit modular integers, Montgomery arithmetic in IMAD.WIDE chains)",
             "data": "synthetic: uniform scalars < p; 2^16 distinct BN254 G1 points tiled to N; device-resident for `value`, host (pageable / pinned) for `e2e`",
             "config": {"workload": f"BN254 G1 MSM 2^{args.logn} per GPU (BASELINE configs[1]), precompute_factor 1, window c={c_used}",
-                       "l2": "inputs (6 GiB at 2^26) exceed the 126 MB L2, no flush needed", "multi_gpu": "point-sharded; one NCCL all-gather of 96 B partials + ec_sum kernel"},
+                       "l2": "inputs (6 GiB at 2^26) exceed the 126 MB L2, no flush needed", "multi_gpu": "point-sharded; one NCCL all-gather of 96 B partials + ec_sum kernel",
+                       "cpu_affinity": f"each rank bound to its GPU's NUMA node (cpus {numa_cpus})" if numa_cpus else "not bound"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "parity_checked": parity,
             "secondary": ntt, "configs": configs,
         }

@@ -12,6 +12,7 @@
 #include "../../include/icicle_b200.h"
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -69,6 +70,7 @@ constexpr size_t COPIER_SLOT_BYTES = 4u << 20;
 
 struct DeviceRes { // per (host thread, device): streams / events / copier contexts reused call after call
   cudaStream_t copy_stream = nullptr;
+  cudaEvent_t blocking_ev = nullptr; // cudaEventBlockingSync: wait for a stream without burning a CPU
   std::vector<cudaEvent_t> events;
   std::vector<CopierCtx*> copiers;
   cudaEvent_t event(size_t i)
@@ -86,8 +88,9 @@ struct DeviceRes { // per (host thread, device): streams / events / copier conte
       CopierCtx* c = new CopierCtx;
       bool ok = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) == cudaSuccess;
       for (int k = 0; k < 2 && ok; k++) {
+        // BlockingSync: a copier thread waiting for its slot sleeps instead of spinning -- several ranks share a CPU quota
         ok = cudaHostAlloc(&c->slot[k], COPIER_SLOT_BYTES, cudaHostAllocDefault) == cudaSuccess &&
-             cudaEventCreateWithFlags(&c->slot_free[k], cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&c->slot_free[k], cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
       }
       if (!ok) {
         (void)cudaGetLastError();
@@ -99,6 +102,12 @@ struct DeviceRes { // per (host thread, device): streams / events / copier conte
     return copiers[i];
   }
 };
+struct DeviceRes;
+inline DeviceRes* device_res();
+// wait for everything enqueued on `s` WITHOUT spinning (long host-pointer calls: the calling thread would otherwise burn a CPU for
+// the whole MSM while several ranks share the container's CPU quota); ~20-50 us wake-up latency, so only used for long calls
+inline cudaError_t stream_sync_blocking(cudaStream_t s);
+
 inline DeviceRes* device_res()
 {
   static thread_local DeviceRes res[64];
@@ -219,7 +228,7 @@ struct PageableCopy {
   {
     const int T = (int)threads.size();
     for (int t = 0; t < T; t++) {
-      while (progress[t].load(std::memory_order_acquire) <= (int)c) std::this_thread::yield();
+      while (progress[t].load(std::memory_order_acquire) <= (int)c) std::this_thread::sleep_for(std::chrono::microseconds(30)); // no busy spin
       if (has_ev[(size_t)t * nchunks + c]) cudaStreamWaitEvent(s, chunk_ev[(size_t)t * nchunks + c], 0);
     }
   }
@@ -231,6 +240,20 @@ struct PageableCopy {
   ~PageableCopy() { join(); }
 };
 
+
+inline cudaError_t stream_sync_blocking(cudaStream_t s)
+{
+  DeviceRes* r = device_res();
+  if (!r) return cudaStreamSynchronize(s);
+  if (!r->blocking_ev && cudaEventCreateWithFlags(&r->blocking_ev, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) {
+    (void)cudaGetLastError();
+    r->blocking_ev = nullptr;
+    return cudaStreamSynchronize(s);
+  }
+  cudaError_t e = cudaEventRecord(r->blocking_ev, s);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(r->blocking_ev);
+}
 
 constexpr size_t RING_MIN_BYTES = 32u << 20;
 

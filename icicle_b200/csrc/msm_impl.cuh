@@ -1005,6 +1005,8 @@ int msm_chunked(const void* scalars, const void* bases, uint32_t n, const b200_m
   prof.finish(any_host ? "msm_pipelined" : "msm_chunked");
   pageable.join();
   if (pageable.failed.load()) rc = B200_COPY_FAILED;
+  // host sources: this call lasts ~100+ ms; wait for it without spinning (ranks share the container's CPU quota)
+  if (rc == B200_SUCCESS && any_host && !(cfg->are_results_on_device && cfg->is_async) && stream_sync_blocking(s) != cudaSuccess) rc = B200_SYNCHRONIZATION_FAILED;
   if (rc == B200_SUCCESS) rc = finish_out(results, d_res, (size_t)PW * 4, cfg->are_results_on_device, cfg->is_async, s);
   if (rc != B200_SUCCESS || any_host) {
     // host sources: the staging areas (Scratch, freed on `s`) must outlive the copies of the private streams
