@@ -69,6 +69,26 @@ struct CopierCtx {
 constexpr size_t COPIER_SLOT_BYTES = 4u << 20;
 
 struct DeviceRes { // per (host thread, device): streams / events / copier contexts reused call after call
+  DeviceRes() = default;
+  DeviceRes(const DeviceRes&) = delete;
+  DeviceRes& operator=(const DeviceRes&) = delete;
+  // thread_local: released when the host thread ends (the multi-GPU orchestrator spawns one thread per device and call); errors
+  // from a runtime that is already shutting down are ignored
+  ~DeviceRes()
+  {
+    for (CopierCtx* c : copiers) {
+      for (int k = 0; k < 2; k++) {
+        if (c->slot[k]) (void)cudaFreeHost(c->slot[k]);
+        if (c->slot_free[k]) (void)cudaEventDestroy(c->slot_free[k]);
+      }
+      if (c->st) (void)cudaStreamDestroy(c->st);
+      delete c;
+    }
+    for (cudaEvent_t e : events) (void)cudaEventDestroy(e);
+    if (blocking_ev) (void)cudaEventDestroy(blocking_ev);
+    if (copy_stream) (void)cudaStreamDestroy(copy_stream);
+    (void)cudaGetLastError();
+  }
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t blocking_ev = nullptr; // cudaEventBlockingSync: wait for a stream without burning a CPU
   std::vector<cudaEvent_t> events;
