@@ -1,3 +1,5 @@
-# GPU-box scratch runner used during development (gpurun -- 'bash tools/gpu_call.sh'): edit per experiment.
+# GPU-box scratch runner used during development (gpurun -- 'bash tools/gpu_call.sh'): edit per experiment.  Default = the round check.
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests/test_gpu_multi.py "tests/test_gpu_fullsize.py::test_bn254_msm_vs_reference" -x -q 2>&1 | tail -4 > gpurun_out/t_last.log; cat gpurun_out/t_last.log; echo "exit=$?"
+timeout 2400 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -8 > gpurun_out/t_full.log; cat gpurun_out/t_full.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 1500 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
