@@ -189,3 +189,86 @@ def test_tuning_table_roundtrip():
     assert capi.lib.b200_get_tuning(b"no_such_knob") == -1
     for lo, hi in ((0, 10), (3, 8), (10, 3)):
         assert ib.shard_range(hi, 4, 0)[0] == 0
+
+
+DIST_NTT_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "oracle")); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import torch, torch.distributed as dist, numpy as np
+import common, port
+from icicle_b200 import utils, shard_range
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, G = dist.get_rank(), dist.get_world_size()
+fp = utils.field_params("babybear"); p = fp["p"]
+a_log, b_log = 3, 4
+A, B, N = 1 << a_log, 1 << b_log, 1 << (a_log + b_log)
+w = pow(fp["rou"], 1 << (fp["two_adicity"] - (a_log + b_log)), p)
+x = common.rand_field_elems("babybear", N, 77, as_ints=True)
+for inverse in (False, True):
+    ww = pow(w, -1, p) if inverse else w
+    # column slab of the A x B row-major view of the natural-order array (b200_ntt_dist_phase1's input layout)
+    lo, hi = shard_range(B, G, rank)
+    cols = hi - lo
+    slab = [[x[r * B + c] for c in range(lo, hi)] for r in range(A)]
+    # phase 1: A-point NTTs down the local columns (the CPU oracle stands in for the GPU), then w_N^(col * k) on element (k, col)
+    wa = pow(w, B, p)
+    for c in range(cols):
+        colv = port.ntt([slab[r][c] for r in range(A)], wa, p, inverse=inverse)
+        for k in range(A):
+            slab[k][c] = colv[k] * pow(ww, (lo + c) * k, p) % p
+    # the ONE exchange: block s (rows of rank s) goes to rank s; every rank receives its blocks in source-rank order
+    rows_lo, rows_hi = shard_range(A, G, rank)
+    send = torch.tensor([[slab[k][c] for c in range(cols)] for k in range(A)], dtype=torch.int64)
+    gathered = [torch.zeros_like(send) for _ in range(G)]
+    dist.all_gather(gathered, send)               # gloo has no all_to_all_single on CPU: gather everything, keep my row block of each source
+    rows = [[0] * B for _ in range(rows_hi - rows_lo)]
+    for src in range(G):
+        slo, shi = shard_range(B, G, src)
+        blk = gathered[src][rows_lo:rows_hi]
+        for k in range(rows_hi - rows_lo):
+            for c in range(shi - slo):
+                rows[k][slo + c] = int(blk[k][c])
+    # phase 2: B-point NTTs along the rows -> X[kb * A + k]; my output is the column slab [B][A/G] of the B x A view of the result
+    wb = pow(w, A, p)
+    out = [port.ntt(rows[k], wb, p, inverse=inverse) for k in range(rows_hi - rows_lo)]
+    full = port.ntt(x, w, p, inverse=inverse)
+    for kb in range(B):
+        for k in range(rows_hi - rows_lo):
+            assert out[k][kb] == full[kb * A + rows_lo + k], (inverse, kb, k)
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_distributed_ntt_decomposition_two_ranks_gloo(tmp_path):
+    """The data movement and index arithmetic of ONE transform spanning ranks (b200_ntt_dist_phase1 -> all-to-all -> phase2:
+    column slabs of the A x B view in, column slabs of the B x A view of the natural-order result out, forward and inverse), run on
+    two gloo ranks with the CPU oracle standing in for the two local GPU phases; the GPU phases themselves are tested against the
+    single-device transform in tests/test_gpu_multi.py."""
+    script = tmp_path / "dist_ntt_worker.py"
+    script.write_text(DIST_NTT_WORKER)
+    port_no = str(30500 + os.getpid() % 1000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port_no, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_multi_gpu_entry_points_fail_loudly_without_a_device():
+    """No CUDA device (this container): the orchestrators must return the reference's error codes, not fall back to anything."""
+    import numpy as np
+    import icicle_b200 as ib
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    s = np.zeros((4, 8), dtype=np.uint32)
+    P = np.zeros((4, 16), dtype=np.uint32)
+    with pytest.raises(ib.IcicleError):
+        ib.msm_multi_gpu(ib.Curve.BN254_G1, s, P, 4, n_devices=2)
+    with pytest.raises(ib.IcicleError):
+        ib.ntt_multi_gpu(ib.Field.BN254_FR, s, 4, ib.NTTDir.kForward, n_devices=2)
+    with pytest.raises(ib.IcicleError):
+        ib.msm(ib.Curve.BN254_G1, s, P, 4)
