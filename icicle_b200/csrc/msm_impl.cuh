@@ -13,7 +13,7 @@
 //
 // GPU schedule (one pass over the scalars, one gather pass over the points):
 //   K6  k_digits        scalar -> signed c-bit digits; emits (bucket key, point index|sign) per (scalar, window)
-//   K7  radix sort      (cub::DeviceRadixSort, library) groups entries by bucket
+//   K7  bucket grouping (cub::DeviceRadixSort above 2^25 entries; own counting sort, msm_sort.cuh, below) groups entries by bucket
 //   K7' pair levels     (msm_pairs.cuh, large inputs) the sorted list is halved up to five times by batched-affine adds
 //                       (6 products per add, inversions shared across the grid) before the bucket accumulation
 //   K8  k_accumulate    each thread owns a fixed SLICE of the sorted entry list and sums runs of equal keys with
@@ -24,7 +24,7 @@
 //   K9  k_bucket_chunks per-chunk running sums: sum_k (k+1)*B_k = triangle + offset*line
 //       k_sum_groups    tree-sum of chunk results per bucket module
 //   K10 k_final         Horner over bucket modules (c doublings each), XYZZ -> projective, out of Montgomery form
-// Host-pointer calls of >= 2^23 points run the same stages chunk by chunk behind the H2D copies (msm_pipelined): every chunk
+// Host-pointer calls of >= 2^23 points run the same stages chunk by chunk behind the H2D copies (msm_chunked): every chunk
 // accumulates into one shared bucket array (window size of the whole MSM), the reduction runs once.
 // The bucket accumulation is integer-multiply bound (6-10 Montgomery products of 140 IMAD.WIDE per point-window) except
 // level 0 of the pair tree, which is bound by HBM's random-sector rate; algorithmic HBM bytes are only |scalar| + |affine|
@@ -530,7 +530,7 @@ inline int choose_pair_levels(uint64_t max_ent, uint64_t max_buckets)
 // Device-resident core: scalars (standard or Montgomery form), points already in Montgomery form, results written to d_res
 // (device).  Everything is enqueued on `s`; nothing here synchronises.
 // `phases`: MSM_ACC = digits .. stitched bucket sums, MSM_RED = bucket reduction + final; the host-pointer pipeline
-// (msm_pipelined) runs MSM_ACC once per point-range chunk into `ext_bkt` (batch == 1) and MSM_RED once at the end.
+// (msm_chunked) runs MSM_ACC once per point-range chunk into `ext_bkt` (batch == 1) and MSM_RED once at the end.
 enum : int { MSM_ACC = 1, MSM_RED = 2, MSM_ALL = 3 };
 
 template <class C>

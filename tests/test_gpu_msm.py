@@ -210,7 +210,7 @@ def test_linearity_large():
 
 
 def test_pipelined_host_path_matches_device_path():
-    """Host-pointer calls with >= 2^23 points take the chunked copy/compute pipeline (msm_pipelined); the result must be the
+    """Host-pointer calls with >= 2^23 points take the chunked copy/compute pipeline (msm_chunked); the result must be the
     same group element as the device-resident single-pass path."""
     C = ib.Curve.BN254_G1
     n = 1 << 23

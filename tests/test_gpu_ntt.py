@@ -134,7 +134,7 @@ def test_errors(domains):
 def test_small_field_tile_pass(field, name, dom_log):
     """The dedicated 4-byte-field pass (csrc/ntt31.cuh, natural order in/out, n >= 2^10) against (a) the oracle port on every
     pass-count / stage-split shape (2^10 .. 2^19: 2 passes of 5..9 stages, 3 passes at 2^19), (b) the generic tile kernel
-    (B200_NTT31_OFF=1) bit for bit at 2^20 x 4, in place and out of place, (c) inverse(forward(x)) == x at the domain size."""
+    (tuning knob ntt31_off = 1) bit for bit at 2^20 x 4, in place and out of place, (c) inverse(forward(x)) == x at the domain size."""
     import os
     import port
     import torch
